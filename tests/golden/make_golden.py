@@ -1,0 +1,237 @@
+"""Generate the golden fixtures under tests/golden/ by EXECUTING THE REFERENCE'S OWN CODE.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python tests/golden/make_golden.py
+The fixtures (*.npz) are committed; tests never import /root/reference.
+
+What runs unmodified from /root/reference:
+  utils/returns_advantages.py  (GAE, MC returns, episode conversion, valid mask / index map, normalisers)
+  utils/rollout_buffer.py      (RolloutBuffer.add + flatten_slice_env_major env-major order)
+  utils/models.py + utils/policy_ops.py + utils/distributions.py (MLPActorCritic / MLPPolicy forward, policy_act)
+  agents/ppo/ppo_agent.py, agents/reinforce/reinforce_agent.py (losses_for_batch + backward + grad norms)
+Shims: the reference's own Lightning stub (tests/conftest.py:15-81) and a stub `gymnasium` module (the real
+package is absent here); neither touches the arithmetic above.  REINFORCE needs config.normalize_advantages
+supplied because the reference reads a field REINFORCEConfig lacks.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _install_shims():
+    sys.path.insert(0, REF)
+    # Lightning stub shipped with the reference's tests
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_conftest", os.path.join(REF, "tests", "conftest.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    # gymnasium stub: only names touched at import time
+    gym = types.ModuleType("gymnasium")
+
+    class _Base:
+        def __init__(self, *a, **k):
+            pass
+
+    for n in ("Wrapper", "ObservationWrapper", "ActionWrapper", "RewardWrapper", "Env"):
+        setattr(gym, n, type(n, (_Base,), {}))
+    spaces = types.ModuleType("gymnasium.spaces")
+    for n in ("Box", "Discrete", "MultiBinary", "MultiDiscrete", "Dict", "Tuple", "Space"):
+        setattr(spaces, n, type(n, (_Base,), {}))
+    vector = types.ModuleType("gymnasium.vector")
+    for n in ("VectorWrapper", "VectorEnv", "SyncVectorEnv", "AsyncVectorEnv"):
+        setattr(vector, n, type(n, (_Base,), {}))
+    gym.spaces, gym.vector = spaces, vector
+    sys.modules.update({"gymnasium": gym, "gymnasium.spaces": spaces, "gymnasium.vector": vector})
+    os.environ.setdefault("WANDB_MODE", "disabled")
+
+
+def golden_returns():
+    from utils import returns_advantages as ra
+
+    cases = {}
+    rng = np.random.default_rng(1234)
+    for name, (T, N, pdone) in {"small": (4, 2, 0.3), "ragged": (17, 5, 0.15), "mid": (64, 33, 0.05), "nodone": (9, 3, 0.0),
+                                "t1": (1, 7, 0.4)}.items():
+        values = rng.standard_normal((T, N)).astype(np.float32)
+        rewards = rng.standard_normal((T, N)).astype(np.float32) if name != "mid" else np.ones((T, N), np.float32)
+        dones = rng.random((T, N)) < pdone
+        timeouts = dones & (rng.random((T, N)) < 0.4)
+        last_values = rng.standard_normal(N).astype(np.float32)
+        boot = np.where(timeouts, rng.standard_normal((T, N)), 0.0).astype(np.float32)
+        gamma, lam = (0.99, 0.95) if name != "ragged" else (0.98, 0.8)
+        adv, ret = ra.compute_batched_gae_advantages_and_returns(values, rewards, dones, timeouts, last_values, boot, gamma, lam)
+        adv0, ret0 = ra.compute_batched_gae_advantages_and_returns(values, rewards, dones, timeouts, last_values, np.zeros_like(boot), gamma, lam)
+        mc_term = ra.compute_batched_mc_returns(rewards, dones, np.zeros_like(timeouts), gamma)
+        mc_keep = ra.compute_batched_mc_returns(rewards, dones, timeouts, gamma)
+        ep_term = ra.convert_returns_to_full_episode(mc_term.copy(), dones, np.zeros_like(timeouts))
+        ep_keep = ra.convert_returns_to_full_episode(mc_keep.copy(), dones, timeouts)
+        vm_t, im_t = ra._build_valid_mask_and_index_map(dones, np.zeros_like(timeouts))
+        vm_k, im_k = ra._build_valid_mask_and_index_map(dones, timeouts)
+        d = dict(values=values, rewards=rewards, dones=dones, timeouts=timeouts, last_values=last_values, boot=boot,
+                 gamma=np.float64(gamma), lam=np.float64(lam), adv=adv, ret=ret, adv0=adv0, ret0=ret0,
+                 mc_term=mc_term, mc_keep=mc_keep, ep_term=ep_term, ep_keep=ep_keep,
+                 norm_adv=ra._normalize_advantages(adv), norm_ret=ra._normalize_returns(ret))
+        for k, v in dict(vm_t=vm_t, im_t=im_t, vm_k=vm_k, im_k=im_k).items():
+            d[k] = np.zeros(0) if v is None else v
+            d[k + "_none"] = np.bool_(v is None)
+        cases[name] = d
+    # the survey's hand-checked case, re-run through the reference
+    values = np.array([[.5, -.2], [.1, .3], [.7, 0], [-.4, .9]], np.float32)
+    rewards = np.array([[1, 1], [1, 1], [1, 0], [1, 1]], np.float32)
+    dones = np.array([[0, 0], [1, 0], [0, 1], [0, 0]], bool)
+    timeouts = np.array([[0, 0], [0, 0], [0, 1], [0, 0]], bool)
+    boot = np.where(timeouts, 2.0, 0.0).astype(np.float32)
+    last_values = np.array([.25, -.5], np.float32)
+    adv, ret = ra.compute_batched_gae_advantages_and_returns(values, rewards, dones, timeouts, last_values, boot, 0.99, 0.95)
+    cases["survey"] = dict(values=values, rewards=rewards, dones=dones, timeouts=timeouts, last_values=last_values, boot=boot,
+                           gamma=np.float64(0.99), lam=np.float64(0.95), adv=adv, ret=ret)
+    for name, d in cases.items():
+        np.savez(os.path.join(OUT, f"returns_{name}.npz"), **d)
+    print("returns:", list(cases))
+
+
+def golden_buffer():
+    from utils.rollout_buffer import RolloutBuffer
+
+    T, N, D = 5, 3, 4
+    rng = np.random.default_rng(7)
+    buf = RolloutBuffer(N, (D,), np.float32, torch.device("cpu"), maxsize=T)
+    start = buf.begin_rollout(T)
+    rec = {k: [] for k in ("obs", "next_obs", "actions", "logps", "values", "rewards", "dones", "timeouts")}
+    for t in range(T):
+        step = dict(obs=rng.standard_normal((N, D)).astype(np.float32), next_obs=rng.standard_normal((N, D)).astype(np.float32),
+                    actions=rng.integers(0, 2, N), logps=rng.standard_normal(N).astype(np.float32),
+                    values=rng.standard_normal(N).astype(np.float32), rewards=rng.standard_normal(N).astype(np.float32),
+                    dones=rng.random(N) < 0.3, timeouts=rng.random(N) < 0.1)
+        buf.add(start + t, step["obs"], step["next_obs"], step["actions"], step["logps"], step["values"], step["rewards"],
+                step["dones"], step["timeouts"])
+        for k, v in step.items():
+            rec[k].append(v)
+    adv = rng.standard_normal((T, N)).astype(np.float32)
+    ret = rng.standard_normal((T, N)).astype(np.float32)
+    traj = buf.flatten_slice_env_major(start, start + T, adv, ret)
+    out = {"in_" + k: np.stack(v) for k, v in rec.items()}
+    out.update(in_adv=adv, in_ret=ret)
+    out.update({"out_" + k: getattr(traj, k).numpy() for k in traj._fields})
+    np.savez(os.path.join(OUT, "buffer_env_major.npz"), **out)
+    print("buffer: ok")
+
+
+def _state_to_params(sd):
+    m = {"backbone.0.weight": "w1", "backbone.0.bias": "b1", "backbone.2.weight": "w2", "backbone.2.bias": "b2",
+         "policy_head.weight": "wp", "policy_head.bias": "bp", "value_head.weight": "wv", "value_head.bias": "bv"}
+    return {m[k]: v.detach().numpy().copy() for k, v in sd.items()}
+
+
+def golden_policy_and_losses():
+    from utils.models import MLPActorCritic, MLPPolicy
+    from utils.policy_ops import policy_act
+    from agents.ppo.ppo_agent import PPOAgent
+    from agents.reinforce.reinforce_agent import REINFORCEAgent
+    import torch.nn as nn
+
+    torch.manual_seed(0)
+    for tag, (D, hidden, A, B) in {"cartpole64": (4, (64, 64), 2, 96), "acrobot128": (6, (128, 128), 3, 64),
+                                   "mcar256": (2, (256, 256), 3, 48), "tiny64": (4, (64,), 2, 40)}.items():
+        model = MLPActorCritic(input_shape=(D,), hidden_dims=hidden, output_shape=(A,), activation="relu")
+        # perturb away from the orthogonal/zero-bias init so every gradient term is exercised
+        with torch.no_grad():
+            for p_ in model.parameters():
+                p_.add_(0.05 * torch.randn_like(p_))
+        obs = torch.randn(B, D)
+        dist, v = model(obs)
+        a_det, lp_det, v_det = policy_act(model, obs, deterministic=True)
+        out = dict(obs=obs.numpy(), logits=dist.logits.detach().numpy(), probs=dist.probs.detach().numpy(),
+                   value=v.detach().numpy(), act_det=a_det.numpy(), logp_det=lp_det.numpy(), value_det=v_det.numpy(),
+                   entropy=dist.entropy().detach().numpy())
+        out.update({"p_" + k: val for k, val in _state_to_params(model.state_dict()).items()})
+
+        # PPO loss + backward through the reference agent (constructed like tests/test_ppo.py:73-87)
+        actions = torch.randint(0, A, (B,))
+        old_logp = dist.log_prob(actions).detach() + 0.15 * torch.randn(B)
+        values_old = v.detach() + 0.3 * torch.randn(B)
+        adv = torch.randn(B) * 2.0 + 0.5
+        ret = values_old + adv
+        for norm in ("batch", "off"):
+            agent = object.__new__(PPOAgent)
+            nn.Module.__init__(agent)
+            agent.config = SimpleNamespace(normalize_advantages=norm, target_kl=None)
+            agent.clip_range, agent.clip_range_vf, agent.vf_coef, agent.ent_coef = 0.2, 0.2, 0.5, 0.01
+            agent.policy_model = model
+            rec = {}
+            agent.metrics_recorder = SimpleNamespace(record=lambda stage, m, rec=rec: rec.update(m))
+            model.zero_grad()
+            model._track_activations = True
+            batch = SimpleNamespace(observations=obs, actions=actions, logprobs=old_logp, values=values_old, advantages=adv, returns=ret)
+            res = agent.losses_for_batch(batch, 0)
+            acts = model.compute_activation_stats()
+            model._track_activations = False
+            res["loss"].backward()
+            gn = model.compute_grad_norms()
+            grads = {k: val for k, val in _state_to_params({n: p_.grad for n, p_ in model.named_parameters()}).items()}
+            out.update({f"ppo_{norm}_loss": res["loss"].detach().numpy()})
+            out.update({f"ppo_{norm}_g_{k}": val for k, val in grads.items()})
+            out.update({f"ppo_{norm}_m_{k}": np.float64(float(val)) for k, val in rec.items()})
+            out.update({f"ppo_{norm}_m_{k}": np.float64(val) for k, val in acts.items()})
+            out.update({f"ppo_{norm}_m_{k}": np.float64(val) for k, val in gn.items()})
+            # clip_grad_norm_ as Lightning's clip_gradients(..., "norm") does
+            total = torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+            out[f"ppo_{norm}_clip_total"] = np.float64(float(total))
+            out.update({f"ppo_{norm}_gc_{k}": val for k, val in _state_to_params({n: p_.grad for n, p_ in model.named_parameters()}).items()})
+        out.update(actions=actions.numpy(), old_logp=old_logp.numpy(), values_old=values_old.numpy(), adv=adv.numpy(), ret=ret.numpy())
+
+        # REINFORCE on a policy-only model
+        pol = MLPPolicy(input_shape=(D,), hidden_dims=hidden, output_shape=(A,), activation="relu")
+        with torch.no_grad():
+            for p_ in pol.parameters():
+                p_.add_(0.05 * torch.randn_like(p_))
+        dist_p, _ = pol(obs)
+        old_logp_p = dist_p.log_prob(actions).detach() + 0.05 * torch.randn(B)
+        out.update({"rp_" + k: val for k, val in _state_to_params(pol.state_dict()).items()})
+        out["r_old_logp"] = old_logp_p.numpy()
+        for targets, nr, na in (("returns", "off", "off"), ("advantages", "off", "batch"), ("returns", "batch", "off")):
+            agent = object.__new__(REINFORCEAgent)
+            nn.Module.__init__(agent)
+            agent.config = SimpleNamespace(normalize_returns=nr, normalize_advantages=na, policy_targets=targets)
+            agent.ent_coef = 0.01
+            agent.policy_model = pol
+            rec = {}
+            agent.metrics_recorder = SimpleNamespace(record=lambda stage, m, rec=rec: rec.update(m))
+            pol.zero_grad()
+            batch = SimpleNamespace(observations=obs, actions=actions, logprobs=old_logp_p, advantages=adv, returns=ret)
+            res = agent.losses_for_batch(batch, 0)
+            res["loss"].backward()
+            key = f"rf_{targets}_{nr}_{na}"
+            out[f"{key}_loss"] = res["loss"].detach().numpy()
+            out.update({f"{key}_g_{k}": val for k, val in _state_to_params({n: p_.grad for n, p_ in pol.named_parameters()}).items()})
+            out.update({f"{key}_m_{k}": np.float64(float(val)) for k, val in rec.items()})
+        np.savez(os.path.join(OUT, f"policy_{tag}.npz"), **out)
+        print("policy/loss:", tag)
+
+
+def golden_masked_categorical():
+    from utils.distributions import MaskedCategorical
+
+    logits = torch.tensor([[0.3, float("-inf"), -1.2, 0.8], [1.0, 2.0, float("-inf"), float("-inf")]])
+    d = MaskedCategorical(logits=logits)
+    a = torch.tensor([2, 1])
+    np.savez(os.path.join(OUT, "masked_categorical.npz"), logits=logits.numpy(), entropy=d.entropy().numpy(),
+             logp=d.log_prob(a).numpy(), actions=a.numpy(), probs=d.probs.numpy())
+    print("masked categorical: ok")
+
+
+if __name__ == "__main__":
+    _install_shims()
+    golden_returns()
+    golden_buffer()
+    golden_masked_categorical()
+    golden_policy_and_losses()
