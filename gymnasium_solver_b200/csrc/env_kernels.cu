@@ -1,0 +1,184 @@
+// env_kernels.cu — GPU-resident vector environments behind the Gymnasium VectorEnv protocol
+// (reset / step as consumed at utils/rollout_collector.py:317 and :504), one thread per env.
+// HBM-bound: state is SoA fp64 ([S][N]) so every load / store of a warp is one contiguous line; the per-step
+// algorithmic traffic is the 98 / 106 / 58 B per env-step of SURVEY.md §8(d).
+#include "env_handle.cuh"
+
+namespace gs {
+
+constexpr int kEnvThreads = 128;
+
+template <int KIND>
+__global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(EnvDev h, float* __restrict__ obs) {
+    const int64_t i = (int64_t)blockIdx.x * kEnvThreads + threadIdx.x;
+    if (i >= h.n) return;
+    EnvRegs e;
+    e.reset_count = h.reset_count[i];
+    env_reset_state<KIND>(e.s, h.params.seed, (uint64_t)(h.params.gid0 + i), e.reset_count);
+    e.reset_count += 1;
+    e.elapsed = 0; e.ep_ret = 0.0; e.ep_len = 0; e.needs_reset = 0;
+    env_store<KIND>(h, i, e);
+    float o[EnvDims<KIND>::D];
+    env_obs<KIND>(e.s, o);
+#pragma unroll
+    for (int d = 0; d < EnvDims<KIND>::D; ++d) obs[i * EnvDims<KIND>::D + d] = o[d];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kEnvThreads)
+env_step_kernel(EnvDev h, const int32_t* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
+                uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, double* __restrict__ ep_return,
+                int32_t* __restrict__ ep_length) {
+    const int64_t i = (int64_t)blockIdx.x * kEnvThreads + threadIdx.x;
+    if (i >= h.n) return;
+    EnvRegs e;
+    env_load<KIND>(h, i, e);
+    float o[EnvDims<KIND>::D];
+    double r, ep_r;
+    bool term, trunc;
+    int ep_l;
+    env_vec_step<KIND>(e, h.params, i, __ldg(actions + i), o, r, term, trunc, ep_r, ep_l);
+    env_store<KIND>(h, i, e);
+    if (EnvDims<KIND>::D == 4) {
+        reinterpret_cast<float4*>(obs)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    } else if (EnvDims<KIND>::D == 2) {
+        reinterpret_cast<float2*>(obs)[i] = make_float2(o[0], o[1]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < EnvDims<KIND>::D; ++d) obs[i * EnvDims<KIND>::D + d] = o[d];
+    }
+    reward[i] = (float)r;
+    terminated[i] = term ? 1 : 0;
+    truncated[i] = trunc ? 1 : 0;
+    if (ep_return) ep_return[i] = ep_r;
+    if (ep_length) ep_length[i] = ep_l;
+}
+
+static int state_dim(int kind) { return kind == GS_ENV_MOUNTAINCAR_V0 ? 2 : 4; }
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" {
+
+int gs_env_obs_dim(int kind) { return kind == GS_ENV_CARTPOLE_V1 ? 4 : (kind == GS_ENV_ACROBOT_V1 ? 6 : (kind == GS_ENV_MOUNTAINCAR_V0 ? 2 : -1)); }
+int gs_env_state_dim(int kind) { return (kind < 0 || kind > 2) ? -1 : state_dim(kind); }
+int gs_env_n_actions(int kind) { return kind == GS_ENV_CARTPOLE_V1 ? 2 : ((kind == GS_ENV_ACROBOT_V1 || kind == GS_ENV_MOUNTAINCAR_V0) ? 3 : -1); }
+int64_t gs_env_num_envs(const gs_env_t* env) { return env ? env->n : -1; }
+
+int gs_env_create(int kind, int64_t n_envs, int64_t env_id_offset, uint64_t seed, int max_episode_steps, int device, gs_env_t** out) {
+    if (!out) GS_FAIL("gs_env_create: out is NULL");
+    if (kind < 0 || kind > 2) GS_FAIL("gs_env_create: unknown env kind %d", kind);
+    if (n_envs <= 0) GS_FAIL("gs_env_create: n_envs must be > 0");
+    if (max_episode_steps < 0) GS_FAIL("gs_env_create: max_episode_steps must be >= 0");
+    GS_CUDA(cudaSetDevice(device));
+    gs_env* e = new gs_env();
+    memset(e, 0, sizeof(gs_env));
+    e->kind = kind; e->device = device; e->n = n_envs;
+    e->params.kind = kind;
+    e->params.max_steps = max_episode_steps > 0 ? max_episode_steps : (kind == GS_ENV_MOUNTAINCAR_V0 ? 200 : 500);
+    e->params.wrapper = 0;
+    e->params.counts = nullptr;
+    e->params.seed = seed;
+    e->params.gid0 = env_id_offset;
+    const size_t n = (size_t)n_envs;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) err = cudaMemset(*p, 0, bytes); } };
+    alloc((void**)&e->state, sizeof(double) * state_dim(kind) * n);
+    alloc((void**)&e->ep_ret, sizeof(double) * n);
+    alloc((void**)&e->elapsed, sizeof(int32_t) * n);
+    alloc((void**)&e->ep_len, sizeof(int32_t) * n);
+    alloc((void**)&e->reset_count, sizeof(uint32_t) * n);
+    alloc((void**)&e->needs_reset, n);
+    if (err != cudaSuccess) {
+        gs_env_destroy(e);
+        GS_FAIL("gs_env_create: allocation failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return 0;
+}
+
+int gs_env_destroy(gs_env_t* e) {
+    if (!e) return 0;
+    cudaFree(e->state); cudaFree(e->ep_ret); cudaFree(e->elapsed); cudaFree(e->ep_len);
+    cudaFree(e->reset_count); cudaFree(e->needs_reset); cudaFree(e->params.counts);
+    delete e;
+    return 0;
+}
+
+int gs_wrapper_attach(gs_env_t* e, int wrapper_kind, const double* params_host, int n_params) {
+    if (!e || !params_host) GS_FAIL("gs_wrapper_attach: NULL argument");
+    if (e->params.wrapper) GS_FAIL("gs_wrapper_attach: env already has wrapper %d (one device wrapper per env)", e->params.wrapper);
+    int need = 0, kind = -1;
+    switch (wrapper_kind) {
+        case GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS: need = 5; kind = GS_ENV_MOUNTAINCAR_V0; break;
+        case GS_WRAP_CARTPOLE_REWARD_SHAPER: need = 3; kind = GS_ENV_CARTPOLE_V1; break;
+        case GS_WRAP_MOUNTAINCAR_REWARD_SHAPER: need = 3; kind = GS_ENV_MOUNTAINCAR_V0; break;
+        default: GS_FAIL("gs_wrapper_attach: unknown wrapper kind %d", wrapper_kind);
+    }
+    if (e->kind != kind) GS_FAIL("gs_wrapper_attach: wrapper %d does not apply to env kind %d", wrapper_kind, e->kind);
+    if (n_params != need) GS_FAIL("gs_wrapper_attach: wrapper %d takes %d params, got %d", wrapper_kind, need, n_params);
+    for (int i = 0; i < 5; ++i) e->params.wp[i] = i < n_params ? params_host[i] : 0.0;
+    if (wrapper_kind == GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS) {
+        const double pb = params_host[0], vb = params_host[1];
+        if (pb < 1 || vb < 1 || pb > 4096 || vb > 4096) GS_FAIL("gs_wrapper_attach: bins out of range");
+        if (params_host[3] < 0 || params_host[3] > 2) GS_FAIL("Unknown bonus_type: %g", params_host[3]);
+        const size_t bytes = sizeof(uint32_t) * (size_t)pb * (size_t)vb * (size_t)e->n;
+        GS_CUDA(cudaSetDevice(e->device));
+        GS_CUDA(cudaMalloc((void**)&e->params.counts, bytes));
+        GS_CUDA(cudaMemset(e->params.counts, 0, bytes));
+    }
+    e->params.wrapper = wrapper_kind;
+    return 0;
+}
+
+int gs_env_set_state(gs_env_t* e, const double* state, const int32_t* elapsed, void* stream) {
+    if (!e || !state) GS_FAIL("gs_env_set_state: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GS_CUDA(cudaMemcpyAsync(e->state, state, sizeof(double) * state_dim(e->kind) * (size_t)e->n, cudaMemcpyDeviceToDevice, st));
+    if (elapsed) GS_CUDA(cudaMemcpyAsync(e->elapsed, elapsed, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int gs_env_get_state(gs_env_t* e, double* state, int32_t* elapsed, void* stream) {
+    if (!e || !state) GS_FAIL("gs_env_get_state: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GS_CUDA(cudaMemcpyAsync(state, e->state, sizeof(double) * state_dim(e->kind) * (size_t)e->n, cudaMemcpyDeviceToDevice, st));
+    if (elapsed) GS_CUDA(cudaMemcpyAsync(elapsed, e->elapsed, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int gs_env_reset(gs_env_t* e, float* obs, void* stream) {
+    if (!e || !obs) GS_FAIL("gs_env_reset: NULL argument");
+    const unsigned blocks = (unsigned)((e->n + kEnvThreads - 1) / kEnvThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const EnvDev h = to_dev(e);
+    switch (e->kind) {
+        case GS_ENV_CARTPOLE_V1: env_reset_kernel<GS_ENV_CARTPOLE_V1><<<blocks, kEnvThreads, 0, st>>>(h, obs); break;
+        case GS_ENV_ACROBOT_V1: env_reset_kernel<GS_ENV_ACROBOT_V1><<<blocks, kEnvThreads, 0, st>>>(h, obs); break;
+        default: env_reset_kernel<GS_ENV_MOUNTAINCAR_V0><<<blocks, kEnvThreads, 0, st>>>(h, obs); break;
+    }
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_env_step(gs_env_t* e, const int32_t* actions, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
+                double* ep_return, int32_t* ep_length, void* stream) {
+    if (!e || !actions || !obs || !reward || !terminated || !truncated) GS_FAIL("gs_env_step: NULL argument");
+    const unsigned blocks = (unsigned)((e->n + kEnvThreads - 1) / kEnvThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const EnvDev h = to_dev(e);
+    switch (e->kind) {
+        case GS_ENV_CARTPOLE_V1:
+            env_step_kernel<GS_ENV_CARTPOLE_V1><<<blocks, kEnvThreads, 0, st>>>(h, actions, obs, reward, terminated, truncated, ep_return, ep_length); break;
+        case GS_ENV_ACROBOT_V1:
+            env_step_kernel<GS_ENV_ACROBOT_V1><<<blocks, kEnvThreads, 0, st>>>(h, actions, obs, reward, terminated, truncated, ep_return, ep_length); break;
+        default:
+            env_step_kernel<GS_ENV_MOUNTAINCAR_V0><<<blocks, kEnvThreads, 0, st>>>(h, actions, obs, reward, terminated, truncated, ep_return, ep_length); break;
+    }
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// returns_kernels.cu — GAE(lambda) and Monte-Carlo return reverse scans, episode conversion, valid-mask / index map,
+// masked moments and normalisation over the time-major (T, N) rollout buffer.
+//
+// Replaces utils/returns_advantages.py (compute_batched_gae_advantages_and_returns :115-155, compute_batched_mc_returns
+// :67-91, convert_returns_to_full_episode :93-113, _build_valid_mask_and_index_map :33-52,
+// _build_idx_map_from_valid_mask :19-30, _normalize_* :55-64) and the RunningStats feeds of
+// utils/rollout_collector.py:415-455.
+//
+// HBM-bound: one thread per env walks t = T-1..0; element (t, n) sits at t*N + n so every warp load is one fully
+// coalesced line.  The recurrence is sequential in t by construction (and evaluated with the reference's exact fp32
+// rounding sequence: results are bit-identical to numpy), so bandwidth comes from keeping UNROLL timesteps of loads in
+// flight per thread; 64-thread CTAs keep the per-SM CTA count balanced (N/64 CTAs over 148 SMs).
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int kScanThreads = 64;
+constexpr int kUnroll = 8;
+
+template <bool HAS_BOOT>
+__global__ void __launch_bounds__(kScanThreads)
+gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+           const uint8_t* __restrict__ timeouts, const float* __restrict__ last_values, const float* __restrict__ boot,
+           int T, int64_t N, float gamma, float gl, float* __restrict__ adv, float* __restrict__ ret) {
+    const int64_t n = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
+    if (n >= N) return;
+    float g = 0.0f;
+    float vnext = __ldg(last_values + n);
+    int t = T - 1;
+    for (; t >= kUnroll - 1; t -= kUnroll) {
+        float v[kUnroll], r[kUnroll], bt[kUnroll];
+        uint8_t d[kUnroll], to[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t o = (int64_t)(t - u) * N + n;
+            v[u] = ldg_stream(values + o);
+            r[u] = ldg_stream(rewards + o);
+            d[u] = ldg_stream(dones + o);
+            to[u] = ldg_stream(timeouts + o);
+            bt[u] = HAS_BOOT ? ldg_stream(boot + o) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t o = (int64_t)(t - u) * N + n;
+            const float nv = (HAS_BOOT && to[u]) ? bt[u] : vnext;
+            const float nt = (d[u] && !to[u]) ? 0.0f : 1.0f;
+            const float delta = fsub(fadd(r[u], fmul(fmul(gamma, nv), nt)), v[u]);
+            g = fadd(delta, fmul(fmul(gl, g), nt));
+            stg_stream(adv + o, g);
+            stg_stream(ret + o, fadd(g, v[u]));
+            vnext = v[u];
+        }
+    }
+    for (; t >= 0; --t) {
+        const int64_t o = (int64_t)t * N + n;
+        const float v = ldg_stream(values + o), r = ldg_stream(rewards + o);
+        const uint8_t d = ldg_stream(dones + o), to = ldg_stream(timeouts + o);
+        const float nv = (HAS_BOOT && to) ? ldg_stream(boot + o) : vnext;
+        const float nt = (d && !to) ? 0.0f : 1.0f;
+        const float delta = fsub(fadd(r, fmul(fmul(gamma, nv), nt)), v);
+        g = fadd(delta, fmul(fmul(gl, g), nt));
+        stg_stream(adv + o, g);
+        stg_stream(ret + o, fadd(g, v));
+        vnext = v;
+    }
+}
+
+// reward-to-go (+ optional per-episode constant) and the last real terminal of every env
+template <bool HAS_TO>
+__global__ void __launch_bounds__(kScanThreads)
+mc_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const uint8_t* __restrict__ timeouts, int T,
+          int64_t N, float gamma, int episode_mode, float* __restrict__ ret, int32_t* __restrict__ last_terminal) {
+    const int64_t n = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
+    if (n >= N) return;
+    float acc = 0.0f;
+    int32_t last = -1;
+    int t = T - 1;
+    for (; t >= kUnroll - 1; t -= kUnroll) {
+        float r[kUnroll];
+        uint8_t d[kUnroll], to[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t o = (int64_t)(t - u) * N + n;
+            r[u] = ldg_stream(rewards + o);
+            d[u] = ldg_stream(dones + o);
+            to[u] = HAS_TO ? ldg_stream(timeouts + o) : (uint8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool term = d[u] && !to[u];
+            if (term && last < 0) last = t - u;
+            acc = fadd(r[u], fmul(gamma, fmul(acc, term ? 0.0f : 1.0f)));
+            ret[(int64_t)(t - u) * N + n] = acc;
+        }
+    }
+    for (; t >= 0; --t) {
+        const int64_t o = (int64_t)t * N + n;
+        const bool term = ldg_stream(dones + o) && !(HAS_TO && ldg_stream(timeouts + o));
+        if (term && last < 0) last = t;
+        acc = fadd(ldg_stream(rewards + o), fmul(gamma, fmul(acc, term ? 0.0f : 1.0f)));
+        ret[o] = acc;
+    }
+    if (last_terminal) last_terminal[n] = last;
+    if (episode_mode) {
+        // every step of a segment takes the reward-to-go of the segment's first step; a segment ends at a real terminal
+        float seg = 0.0f;
+        bool start = true;
+        for (int tt = 0; tt < T; ++tt) {
+            const int64_t o = (int64_t)tt * N + n;
+            if (start) seg = ret[o];
+            else ret[o] = seg;
+            start = __ldg(dones + o) && !(HAS_TO && __ldg(timeouts + o));
+        }
+    }
+}
+
+// ---- valid mask / index map ------------------------------------------------------------------------------------------
+// inc[e] = largest env index e' <= e that has a real terminal (-1 if none): block-local inclusive max-scan + block maxima
+__global__ void valid_scan_local_kernel(const int32_t* __restrict__ last_terminal, int64_t N, int32_t* __restrict__ inc,
+                                        int32_t* __restrict__ block_max, unsigned long long* __restrict__ n_valid,
+                                        int32_t* __restrict__ first_env) {
+    __shared__ int32_t warp_max_s[32];
+    __shared__ unsigned long long cnt_s[32];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t lt = e < N ? last_terminal[e] : -1;
+    int32_t v = lt >= 0 ? (int32_t)e : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = max(v, u);
+    }
+    if (lane == 31) warp_max_s[w] = v;
+    unsigned long long c = warp_sum((unsigned long long)(lt + 1));
+    if (lane == 0) cnt_s[w] = c;
+    __syncthreads();
+    int32_t prefix = -1;
+    for (int i = 0; i < w; ++i) prefix = max(prefix, warp_max_s[i]);
+    v = max(v, prefix);
+    if (e < N) inc[e] = v;
+    if (threadIdx.x == blockDim.x - 1) block_max[blockIdx.x] = v;
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += cnt_s[i];
+        if (tot) atomicAdd(n_valid, tot);
+    }
+    if (lt >= 0) atomicMin(first_env, (int32_t)e);
+}
+
+__global__ void valid_scan_blocks_kernel(int32_t* __restrict__ block_max, int n_blocks) {
+    // exclusive max-scan over block maxima, in place (n_blocks <= N/1024: a few thousand entries)
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int32_t run = -1;
+    for (int b = 0; b < n_blocks; ++b) {
+        const int32_t m = block_max[b];
+        block_max[b] = run;
+        run = max(run, m);
+    }
+}
+
+__global__ void valid_apply_kernel(const int32_t* __restrict__ last_terminal, const int32_t* __restrict__ inc,
+                                   const int32_t* __restrict__ block_prefix, const int32_t* __restrict__ first_env, int T,
+                                   int64_t N, uint8_t* __restrict__ valid_mask, int64_t* __restrict__ idx_map) {
+    const int64_t total = N * (int64_t)T;
+    const int32_t fe = *first_env;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / T;
+        const int t = (int)(i - e * T);
+        const int32_t lt = last_terminal[e];
+        int64_t target;
+        uint8_t valid = 0;
+        if (lt >= 0) {
+            valid = t <= lt;
+            target = valid ? i : e * T + lt;
+        } else {
+            const int32_t pe = max(inc[e], block_prefix[e >> 10]);
+            if (pe >= 0) target = (int64_t)pe * T + last_terminal[pe];
+            else target = fe < 0x7fffffff ? (int64_t)fe * T : 0;   // prefix before the first valid entry -> first valid
+        }
+        if (valid_mask) valid_mask[i] = valid;
+        idx_map[i] = target;
+    }
+}
+__global__ void valid_init_kernel(unsigned long long* n_valid, int32_t* first_env) { *n_valid = 0ull; *first_env = 0x7fffffff; }
+
+// ---- moments / normalise ------------------------------------------------------------------------------------------------
+__global__ void moments_kernel(const float* __restrict__ x, const int32_t* __restrict__ last_terminal, int T, int64_t N,
+                               double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double s = 0.0, s2 = 0.0, c = 0.0;
+    const int64_t total = N * (int64_t)T;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        bool use = true;
+        if (last_terminal) {
+            const int64_t t = i / N, n = i - t * N;
+            use = t <= last_terminal[n];
+        }
+        if (use) {
+            const double v = (double)ldg_stream(x + i);
+            s += v; s2 += v * v; c += 1.0;
+        }
+    }
+    s = block_sum(s, scratch);
+    s2 = block_sum(s2, scratch);
+    c = block_sum(c, scratch);
+    if (threadIdx.x == 0 && c > 0.0) { atomicAdd(out, s); atomicAdd(out + 1, s2); atomicAdd(out + 2, c); }
+}
+
+__global__ void normalize_kernel(const float* __restrict__ x, int64_t n, const double* __restrict__ mom, float eps, int mode,
+                                 float* __restrict__ y) {
+    const double cnt = mom[2] > 0.0 ? mom[2] : 1.0;
+    const double mu = mom[0] / cnt;
+    double var = mom[1] / cnt - mu * mu;   // population variance (numpy .std())
+    var = var > 0.0 ? var : 0.0;
+    const float mean = (float)mu;
+    const float denom = mode == 0 ? (float)sqrt(var) + eps : 1.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = mode == 0 ? (x[i] - mean) / denom : x[i] - mean;
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" {
+
+int gs_gae(const float* values, const float* rewards, const uint8_t* dones, const uint8_t* timeouts, const float* last_values,
+           const float* bootstrapped, int T, int64_t N, double gamma, double gae_lambda, float* adv, float* ret, void* stream) {
+    if (!values || !rewards || !dones || !timeouts || !last_values || !adv || !ret) GS_FAIL("gs_gae: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_gae: empty rollout (T=%d, N=%lld)", T, (long long)N);
+    const unsigned blocks = (unsigned)((N + kScanThreads - 1) / kScanThreads);
+    const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bootstrapped) gae_kernel<true><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, bootstrapped, T, N, g, gl, adv, ret);
+    else gae_kernel<false><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, nullptr, T, N, g, gl, adv, ret);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_mc_returns(const float* rewards, const uint8_t* dones, const uint8_t* timeouts, int T, int64_t N, double gamma,
+                  int episode_mode, float* ret, int32_t* last_terminal, void* stream) {
+    if (!rewards || !dones || !ret) GS_FAIL("gs_mc_returns: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_mc_returns: empty rollout (T=%d, N=%lld)", T, (long long)N);
+    const unsigned blocks = (unsigned)((N + kScanThreads - 1) / kScanThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (timeouts) mc_kernel<true><<<blocks, kScanThreads, 0, st>>>(rewards, dones, timeouts, T, N, (float)gamma, episode_mode, ret, last_terminal);
+    else mc_kernel<false><<<blocks, kScanThreads, 0, st>>>(rewards, dones, nullptr, T, N, (float)gamma, episode_mode, ret, last_terminal);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t gs_valid_index_map_workspace_bytes(int64_t N) {
+    const int64_t nb = (N + 1023) / 1024;
+    return ((N * 4 + 255) / 256 + (nb * 4 + 255) / 256 + 1) * 256;
+}
+
+int gs_valid_index_map(const int32_t* last_terminal, int T, int64_t N, uint8_t* valid_mask, int64_t* idx_map, int64_t* n_valid,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!last_terminal || !idx_map || !n_valid || !workspace) GS_FAIL("gs_valid_index_map: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_valid_index_map: empty rollout");
+    if (N >= (1ll << 31)) GS_FAIL("gs_valid_index_map: N too large");
+    if (workspace_bytes < gs_valid_index_map_workspace_bytes(N)) GS_FAIL("gs_valid_index_map: workspace too small");
+    const int64_t nb = (N + 1023) / 1024;
+    char* p = (char*)workspace;
+    int32_t* inc = (int32_t*)p; p += (N * 4 + 255) / 256 * 256;
+    int32_t* block_max = (int32_t*)p; p += (nb * 4 + 255) / 256 * 256;
+    int32_t* first_env = (int32_t*)p;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    valid_init_kernel<<<1, 1, 0, st>>>((unsigned long long*)n_valid, first_env);
+    valid_scan_local_kernel<<<(unsigned)nb, 1024, 0, st>>>(last_terminal, N, inc, block_max, (unsigned long long*)n_valid, first_env);
+    valid_scan_blocks_kernel<<<1, 32, 0, st>>>(block_max, (int)nb);
+    const int64_t total = N * (int64_t)T;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = 8ll * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    valid_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(last_terminal, inc, block_max, first_env, T, N, valid_mask, idx_map);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_moments(const float* x, const int32_t* last_terminal, int T, int64_t N, double* out, void* stream) {
+    if (!x || !out) GS_FAIL("gs_moments: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_moments: empty input");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    const int64_t total = N * (int64_t)T;
+    int64_t blocks = (total + 1023) / 1024;
+    const int64_t cap = 8ll * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, last_terminal, T, N, out);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_normalize(const float* x, int64_t n, const double* moments, float eps, int mode, float* y, void* stream) {
+    if (!x || !y || !moments) GS_FAIL("normalize: NULL argument");
+    if (n <= 0) GS_FAIL("normalize: empty input");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    int64_t blocks = (n + 1023) / 1024;
+    const int64_t cap = 8ll * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, moments, eps, mode, y);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_normalize(const float* x, int64_t n, const double* moments, float eps, float* y, void* stream) {
+    return launch_normalize(x, n, moments, eps, 0, y, stream);
+}
+int gs_shift_by_mean(const float* x, int64_t n, const double* moments, float* y, void* stream) {
+    return launch_normalize(x, n, moments, 0.f, 1, y, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,761 @@
+// update_kernels.cu — fused minibatch forward + loss + backward for PPO and REINFORCE, the deterministic gradient /
+// metric reduction, the global-norm clip and a graph-capturable Adam.
+//
+// Replaces: RolloutCollector.slice_trajectories gather (utils/rollout_collector.py:657-682),
+//           PPOAgent.losses_for_batch (agents/ppo/ppo_agent.py:21-152), REINFORCEAgent.losses_for_batch
+//           (agents/reinforce/reinforce_agent.py:11-88), loss.backward(), BaseModel activation hooks
+//           (utils/models.py:121-194), compute_grad_norms + clip_gradients (agents/base_agent.py:591-621).
+#include "mlp_tile.cuh"
+
+namespace gs {
+
+enum { ALGO_PPO = 0, ALGO_REINFORCE = 1 };
+
+// per-CTA partial sums (doubles)
+enum {
+    PM_SURR = 0, PM_VLOSS, PM_ENT, PM_CLIPF, PM_CLIPF_VF, PM_RV, PM_RV2, PM_R, PM_R2, PM_KL, PM_AKL, PM_ADVN, PM_ADVN2,
+    PM_TGT, PM_TGT2, PM_RETN, PM_RETN2, PM_Z0, PM_Z0SQ, PM_Z1, PM_Z1SQ, PM_COUNT, PM_N
+};
+
+struct BatchDev {
+    int64_t n;
+    const int64_t* idx;
+    uint64_t perm_key;
+    int64_t perm_offset, perm_len;
+    const int64_t* idx_map;
+    int T, D;
+    int64_t N;
+    const float* obs;
+    const int32_t* actions;
+    const float *logp_old, *values_old, *adv, *ret;
+};
+
+struct HpDev {
+    float clip_lo, clip_hi, clip_vf, vf_coef, ent_coef;
+    int normalize_adv, normalize_ret, policy_targets;
+};
+
+__device__ __forceinline__ int64_t sample_offset(const BatchDev& b, int64_t pos) {
+    int64_t i;
+    if (b.idx) i = b.idx[pos];
+    else if (b.perm_len > 0) i = (int64_t)feistel_permute((uint64_t)(b.perm_offset + pos), (uint64_t)b.perm_len, b.perm_key);
+    else i = b.perm_offset + pos;
+    if (b.idx_map) i = b.idx_map[i];
+    const int64_t e = i / b.T, t = i - e * b.T;   // env-major id -> (env, step)
+    return t * b.N + e;                            // time-major offset
+}
+
+// mean / (std + eps) denominators from raw moments {sum, sumsq, count}; unbiased std like torch.std
+__device__ __forceinline__ void norm_consts(const double* mom, float& mean, float& denom) {
+    const double n = mom[2];
+    const double mu = mom[0] / n;
+    double var = (mom[1] - mom[0] * mu) / (n - 1.0);
+    var = var > 0.0 ? var : 0.0;
+    mean = (float)mu;
+    denom = (float)sqrt(var) + 1e-8f;
+}
+
+// ---- the fused kernel -----------------------------------------------------------------------------------------------
+template <class C, int ALGO, bool TRACK>
+__global__ void __launch_bounds__(kThreads, (C::kSmemFloats * 4 <= 110 * 1024) ? 2 : 1)
+update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom, const double* __restrict__ ret_mom,
+              float* __restrict__ grad_partials /* persist: [grid][P] */, float* __restrict__ grads_atomic /* else: [P] */,
+              double* __restrict__ metric_partials /* [grid][PM_N] */, uint32_t* __restrict__ dead) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    constexpr int S = C::S, TS = C::TS, HL = C::HL;
+    const ParamOffsets po = param_offsets(m.D, C::H1, C::H2, m.A, m.has_value);
+
+    load_resident<C>(sm, m);
+
+    float adv_mean = 0.f, adv_den = 1.f, ret_mean = 0.f, ret_den = 1.f;
+    if (hp.normalize_adv) norm_consts(adv_mom, adv_mean, adv_den);
+    if (hp.normalize_ret) norm_consts(ret_mom, ret_mean, ret_den);
+    const float invB = 1.0f / (float)b.n;
+
+    // persistent wgrad accumulators (registers for the whole kernel when C::kPersist)
+    float acc_w2[8][4];
+    float acc_h[kNH];
+    constexpr int G1 = kThreads / C::H1;        // thread groups splitting the 8 padded inputs of layer 1
+    constexpr int R1 = kDP / G1;                // inputs per thread
+    constexpr int GL = kThreads / HL;           // thread groups splitting the samples for head / bias sums
+    float acc_w1[R1];
+    float acc_b1 = 0.f, acc_b2 = 0.f, acc_bh = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc_w2[i][c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kNH; ++r) acc_h[r] = 0.f;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) acc_w1[r] = 0.f;
+
+    float pm[PM_N];
+#pragma unroll
+    for (int i = 0; i < PM_N; ++i) pm[i] = 0.f;
+    ActStats st;
+    st.sum[0] = st.sum[1] = st.sumsq[0] = st.sumsq[1] = 0.f;
+    st.dead = dead;
+
+    const int64_t n_tiles = (b.n + S - 1) / S;
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t pos0 = tile * S;
+        const int valid_rows = (int)min((int64_t)S, b.n - pos0);
+        // ---- gather (one thread per sample) -------------------------------------------------------------------
+        int a_s = 0;
+        float lp_old = 0.f, v_old = 0.f, adv_s = 0.f, ret_s = 0.f;
+        if (tid < S) {
+            float x[kDP];
+#pragma unroll
+            for (int d = 0; d < kDP; ++d) x[d] = 0.f;
+            if (tid < valid_rows) {
+                const int64_t off = sample_offset(b, pos0 + tid);
+                const float* o = b.obs + off * b.D;
+                if (b.D == 4) {
+                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(o));
+                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+                } else if (b.D == 2) {
+                    const float2 v2 = __ldg(reinterpret_cast<const float2*>(o));
+                    x[0] = v2.x; x[1] = v2.y;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < kDP; ++d)
+                        if (d < b.D) x[d] = __ldg(o + d);
+                }
+                a_s = __ldg(b.actions + off);
+                lp_old = __ldg(b.logp_old + off);
+                adv_s = __ldg(b.adv + off);
+                ret_s = __ldg(b.ret + off);
+                if (ALGO == ALGO_PPO) v_old = __ldg(b.values_old + off);
+            }
+            float4* xr = reinterpret_cast<float4*>(sm + C::oXS + tid * kLDX);
+            xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+            xr[1] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        __syncthreads();
+
+        // ---- forward ------------------------------------------------------------------------------------------
+        forward_backbone<C, TRACK>(sm, m, valid_rows, &st);
+
+        // ---- heads + loss + dLoss/d(head outputs) (one thread per sample) -------------------------------------
+        if (tid < S) {
+            float g[kNH] = {0.f, 0.f, 0.f, 0.f};
+            if (tid < valid_rows) {
+                float out[kNH];
+                forward_heads<C>(sm, tid, out);
+                const int A = m.A;
+                float lp[3] = {0.f, 0.f, 0.f}, p[3] = {0.f, 0.f, 0.f};
+                log_softmax(out, A, lp);
+                float H = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < A) { p[k] = expf(lp[k]); H -= p[k] * lp[k]; }
+                const float logp = a_s == 0 ? lp[0] : (a_s == 1 ? lp[1] : lp[2]);
+                float dlogp;
+                if (ALGO == ALGO_PPO) {
+                    const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
+                    const float ratio = expf(logp - lp_old);
+                    const float rc = fminf(fmaxf(ratio, hp.clip_lo), hp.clip_hi);
+                    const float s1 = adv_n * ratio, s2 = adv_n * rc;
+                    const bool inrange = (ratio >= hp.clip_lo) && (ratio <= hp.clip_hi);
+                    dlogp = (inrange || s1 < s2) ? -(s1 * invB) : 0.f;
+                    pm[PM_SURR] += fminf(s1, s2);
+                    pm[PM_CLIPF] += inrange ? 0.f : 1.f;
+                    pm[PM_ADVN] += adv_n; pm[PM_ADVN2] = fmaf(adv_n, adv_n, pm[PM_ADVN2]);
+                    // clipped value loss
+                    const float v = A == 2 ? out[2] : out[3];
+                    const float vd = v - v_old;
+                    const float eu = v - ret_s, lu = eu * eu;
+                    const float vc = v_old + fminf(fmaxf(vd, -hp.clip_vf), hp.clip_vf);
+                    const float ec = vc - ret_s, lc = ec * ec;
+                    const bool in_vf = (vd >= -hp.clip_vf) && (vd <= hp.clip_vf);
+                    const float gc = in_vf ? 2.f * ec : 0.f;
+                    const float dv = lu > lc ? 2.f * eu : (lu < lc ? gc : 0.5f * (2.f * eu) + 0.5f * gc);
+                    const float gv = hp.vf_coef * dv * invB;
+                    if (A == 2) g[2] = gv; else g[3] = gv;
+                    pm[PM_VLOSS] += fmaxf(lu, lc);
+                    pm[PM_CLIPF_VF] += in_vf ? 0.f : 1.f;
+                    const float rv = ret_s - v;
+                    pm[PM_RV] += rv; pm[PM_RV2] = fmaf(rv, rv, pm[PM_RV2]);
+                    pm[PM_R] += ret_s; pm[PM_R2] = fmaf(ret_s, ret_s, pm[PM_R2]);
+                } else {
+                    const float ret_n = hp.normalize_ret ? (ret_s - ret_mean) / ret_den : ret_s;
+                    const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
+                    const float tgt = hp.policy_targets == 0 ? ret_n : adv_n;
+                    dlogp = -(tgt * invB);
+                    pm[PM_SURR] += logp * tgt;
+                    pm[PM_TGT] += tgt; pm[PM_TGT2] = fmaf(tgt, tgt, pm[PM_TGT2]);
+                    pm[PM_ADVN] += adv_n; pm[PM_ADVN2] = fmaf(adv_n, adv_n, pm[PM_ADVN2]);
+                    pm[PM_RETN] += ret_n; pm[PM_RETN2] = fmaf(ret_n, ret_n, pm[PM_RETN2]);
+                }
+                const float ec_b = hp.ent_coef * invB;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < A) g[k] = dlogp * ((k == a_s ? 1.f : 0.f) - p[k]) + ec_b * p[k] * (lp[k] + H);
+                pm[PM_ENT] += H;
+                pm[PM_KL] += lp_old - logp;
+                const float dcl = fminf(fmaxf(logp - lp_old, -20.f), 20.f);   // utils/torch.py:115-118
+                const float r2 = expf(dcl);
+                pm[PM_AKL] += (r2 - 1.f) - logf(r2);
+                pm[PM_COUNT] += 1.f;
+            }
+            *reinterpret_cast<float4*>(sm + C::oG + tid * kNH) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        __syncthreads();
+
+        float* hL = sm + (C::H2 > 0 ? C::oA2 : C::oA1);
+        const float* G = sm + C::oG;
+        // ---- head wgrad: dWh[r][k] += sum_s g[s][r] * hL[s][k] ---------------------------------------------------
+        {
+            const int k = tid % HL, sg = tid / HL;
+            float loc[kNH] = {0.f, 0.f, 0.f, 0.f};
+            for (int s = sg; s < S; s += GL) {
+                const float h = hL[s * C::LDL + k];
+                const float4 g4 = *reinterpret_cast<const float4*>(G + s * kNH);
+                loc[0] = fmaf(g4.x, h, loc[0]); loc[1] = fmaf(g4.y, h, loc[1]);
+                loc[2] = fmaf(g4.z, h, loc[2]); loc[3] = fmaf(g4.w, h, loc[3]);
+            }
+            if (C::kPersist) {
+#pragma unroll
+                for (int r = 0; r < kNH; ++r) acc_h[r] += loc[r];
+            } else {
+                for (int r = 0; r < m.A; ++r) atomicAdd(grads_atomic + po.wp + (int64_t)r * HL + k, loc[r]);
+                if (m.has_value) atomicAdd(grads_atomic + po.wv + k, loc[m.A]);
+            }
+            if (tid < kNH) {  // head biases
+                float sgm = 0.f;
+                for (int s = 0; s < S; ++s) sgm += G[s * kNH + tid];
+                if (C::kPersist) acc_bh += sgm;
+                else if (tid < m.A) atomicAdd(grads_atomic + po.bp + tid, sgm);
+                else if (tid == m.A && m.has_value) atomicAdd(grads_atomic + po.bv, sgm);
+            }
+        }
+        __syncthreads();
+        // ---- dZL = (G @ Wh) * act'(hL), in place over hL -------------------------------------------------------------
+        {
+            const float* wh = sm + C::oWH;
+#pragma unroll 1
+            for (int nc = 0; nc < HL / 64; ++nc) {
+                const int col = nc * 64 + 4 * tx;
+                float4 w[kNH];
+#pragma unroll
+                for (int r = 0; r < kNH; ++r) w[r] = *reinterpret_cast<const float4*>(wh + r * C::LDL + col);
+#pragma unroll
+                for (int j = 0; j < TS; ++j) {
+                    const int s = ty * TS + j;
+                    const float4 g4 = *reinterpret_cast<const float4*>(G + s * kNH);
+                    float4* hp4 = reinterpret_cast<float4*>(hL + s * C::LDL + col);
+                    const float4 h = *hp4;
+                    float4 d;
+                    d.x = g4.x * w[0].x + g4.y * w[1].x + g4.z * w[2].x + g4.w * w[3].x;
+                    d.y = g4.x * w[0].y + g4.y * w[1].y + g4.z * w[2].y + g4.w * w[3].y;
+                    d.z = g4.x * w[0].z + g4.y * w[1].z + g4.z * w[2].z + g4.w * w[3].z;
+                    d.w = g4.x * w[0].w + g4.y * w[1].w + g4.z * w[2].w + g4.w * w[3].w;
+                    d.x *= act_bwd(h.x, m.act); d.y *= act_bwd(h.y, m.act);
+                    d.z *= act_bwd(h.z, m.act); d.w *= act_bwd(h.w, m.act);
+                    *hp4 = d;
+                }
+            }
+        }
+        __syncthreads();
+
+        if (C::H2 > 0) {
+            const float* dZ2 = sm + C::oA2;
+            float* a1 = sm + C::oA1;
+            // ---- layer-2 bias + weight gradients -----------------------------------------------------------------------
+            {
+                const int n = tid % C::HL, sg = tid / C::HL;
+                float sgm = 0.f;
+                for (int s = sg; s < S; s += GL) sgm += dZ2[s * C::LD2 + n];
+                if (C::kPersist) acc_b2 += sgm;
+                else atomicAdd(grads_atomic + po.b2 + n, sgm);
+            }
+            {
+                const int half = tid >> 7, t = tid & 127, tn = t >> 4, tk = t & 15;
+                if (C::kPersist) {
+                    tile_tn<S>(acc_w2, dZ2, C::LD2, a1, C::LD1, tn, tk, half);
+                } else {
+#pragma unroll 1
+                    for (int nb = 0; nb < C::H2 / 64; ++nb)
+#pragma unroll 1
+                        for (int kb = 0; kb < C::H1 / 64; ++kb) {
+                            float acc[8][4];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+                            tile_tn<S>(acc, dZ2 + nb * 64, C::LD2, a1 + kb * 64, C::LD1, tn, tk, half);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    atomicAdd(grads_atomic + po.w2 + (int64_t)(nb * 64 + 8 * tn + i) * C::H1 + kb * 64 + 4 * tk + c, acc[i][c]);
+                        }
+                }
+            }
+            __syncthreads();
+            // ---- dZ1 = (dZ2 @ W2) * act'(h1), in place over a1 ------------------------------------------------------------
+#pragma unroll 1
+            for (int kc = 0; kc < C::H1 / 64; ++kc) {
+                float acc[TS][4];
+#pragma unroll
+                for (int j = 0; j < TS; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll 1
+                for (int nc = 0; nc < C::H2 / 64; ++nc) {
+                    if (!C::kResidentW2) {
+                        __syncthreads();
+                        stage_w64(sm + C::oWB, m.w2, C::H1, nc * 64, kc * 64);
+                        __syncthreads();
+                    }
+                    tile_nn<TS>(acc, dZ2 + nc * 64, C::LD2, sm + C::oWB, kWLD, tx, ty);
+                }
+#pragma unroll
+                for (int j = 0; j < TS; ++j) {
+                    float4* hp4 = reinterpret_cast<float4*>(a1 + (ty * TS + j) * C::LD1 + kc * 64 + 4 * tx);
+                    const float4 h = *hp4;
+                    *hp4 = make_float4(acc[j][0] * act_bwd(h.x, m.act), acc[j][1] * act_bwd(h.y, m.act),
+                                       acc[j][2] * act_bwd(h.z, m.act), acc[j][3] * act_bwd(h.w, m.act));
+                }
+            }
+            __syncthreads();
+        }
+        // ---- layer-1 weight / bias gradients: dW1[n][d] += sum_s dZ1[s][n] * x[s][d] --------------------------------------
+        {
+            const float* dZ1 = sm + C::oA1;
+            const float* xs = sm + C::oXS;
+            const int n = tid % C::H1, dg = tid / C::H1;
+            float loc[R1];
+#pragma unroll
+            for (int r = 0; r < R1; ++r) loc[r] = 0.f;
+            float sb = 0.f;
+            for (int s = 0; s < S; ++s) {
+                const float dz = dZ1[s * C::LD1 + n];
+#pragma unroll
+                for (int r = 0; r < R1; ++r) loc[r] = fmaf(dz, xs[s * kLDX + dg * R1 + r], loc[r]);
+                sb += dz;
+            }
+            if (C::kPersist) {
+#pragma unroll
+                for (int r = 0; r < R1; ++r) acc_w1[r] += loc[r];
+                if (dg == 0) acc_b1 += sb;
+            } else {
+#pragma unroll
+                for (int r = 0; r < R1; ++r)
+                    if (dg * R1 + r < m.D) atomicAdd(grads_atomic + po.w1 + (int64_t)n * m.D + dg * R1 + r, loc[r]);
+                if (dg == 0) atomicAdd(grads_atomic + po.b1 + n, sb);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- fold the register accumulators of this CTA into one partial gradient vector (deterministic order) ----------
+    if (C::kPersist) {
+        float* gsm = sm;  // reuse the activation tiles: P floats
+        const int P = (int)po.total;
+        for (int i = tid; i < P; i += kThreads) gsm[i] = 0.f;
+        __syncthreads();
+        const int half = tid >> 7, t = tid & 127, tn = t >> 4, tk = t & 15;
+        const int kh = tid % HL, sg = tid / HL;
+        constexpr int ROUNDS = GL > 2 ? GL : 2;
+        for (int round = 0; round < ROUNDS; ++round) {
+            if (C::H2 > 0 && half == round) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) gsm[po.w2 + (8 * tn + i) * C::H1 + 4 * tk + c] += acc_w2[i][c];
+            }
+            if (sg == round) {
+                for (int r = 0; r < m.A; ++r) gsm[po.wp + r * HL + kh] += acc_h[r];
+                if (m.has_value) gsm[po.wv + kh] += acc_h[m.A];
+                if (C::H2 > 0) gsm[po.b2 + kh] += acc_b2;
+            }
+            __syncthreads();
+        }
+        {
+            const int n = tid % C::H1, dg = tid / C::H1;
+#pragma unroll
+            for (int r = 0; r < R1; ++r)
+                if (dg * R1 + r < m.D) gsm[po.w1 + n * m.D + dg * R1 + r] = acc_w1[r];
+            if (dg == 0) gsm[po.b1 + n] = acc_b1;
+            if (tid < m.A) gsm[po.bp + tid] = acc_bh;
+            else if (tid == m.A && m.has_value) gsm[po.bv] = acc_bh;
+        }
+        __syncthreads();
+        float* out = grad_partials + (size_t)blockIdx.x * P;
+        for (int i = tid; i < P; i += kThreads) out[i] = gsm[i];
+    }
+
+    // ---- metric partials: warp shuffle, then one cross-warp pass through shared memory ---------------------------------
+    if (TRACK) { pm[PM_Z0] = st.sum[0]; pm[PM_Z0SQ] = st.sumsq[0]; pm[PM_Z1] = st.sum[1]; pm[PM_Z1SQ] = st.sumsq[1]; }
+    __syncthreads();
+    {
+        double* red = reinterpret_cast<double*>(sm + ((C::kPersist ? (int)po.total : 0) + 3) / 4 * 4 + 4);  // past gsm, 16 B aligned
+        const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+        for (int i = 0; i < PM_N; ++i) {
+            const double v = warp_sum((double)pm[i]);
+            if (lane == 0) red[w * PM_N + i] = v;
+        }
+        __syncthreads();
+        if (tid < PM_N) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < kThreads / 32; ++ww) s += red[ww * PM_N + tid];
+            metric_partials[(size_t)blockIdx.x * PM_N + tid] = s;
+        }
+    }
+}
+
+// ---- stage 2: ordered reduction over CTAs + metric finalisation ---------------------------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int64_t P, float* __restrict__ grads) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * P + i];
+    grads[i] = s;
+}
+
+__global__ void finalize_metrics_kernel(const double* __restrict__ partials, int n_cta, int algo, int H1, int H2, int track,
+                                        float vf_coef, float ent_coef, int normalize_adv, int normalize_ret,
+                                        const uint32_t* __restrict__ dead, double* __restrict__ metrics) {
+    __shared__ double tot[PM_N];
+    __shared__ double dead_stats[4];
+    const int tid = threadIdx.x;
+    if (tid < PM_N) {
+        double s = 0.0;
+        for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * PM_N + tid];
+        tot[tid] = s;
+    }
+    if (tid == 32 && track) {  // dead-neuron fractions per hooked layer: mean and max over neurons
+        for (int l = 0; l < 2; ++l) {
+            const int H = l == 0 ? H1 : H2, base = l == 0 ? 0 : H1;
+            double sum = 0.0, mx = 0.0;
+            for (int n = 0; n < H; ++n) { const double c = (double)dead[base + n]; sum += c; mx = c > mx ? c : mx; }
+            dead_stats[2 * l] = sum; dead_stats[2 * l + 1] = mx;
+        }
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const double B = tot[PM_COUNT];
+    const double ent = tot[PM_ENT] / B;
+    auto ustd = [](double s, double s2, double n) { double v = (s2 - s * s / n) / (n - 1.0); return sqrt(v > 0.0 ? v : 0.0); };
+    for (int i = 0; i < GS_M_GRAD_NORM_ALL; ++i) metrics[i] = 0.0;
+    metrics[GS_M_RET_NORM_MEAN] = metrics[GS_M_RET_NORM_STD] = 0.0;
+    metrics[GS_M_BATCH_COUNT] = B;
+    const double policy_loss = -tot[PM_SURR] / B;
+    metrics[GS_M_LOSS_POLICY] = policy_loss;
+    metrics[GS_M_LOSS_ENTROPY] = -ent;
+    metrics[GS_M_ENTROPY] = ent;
+    metrics[GS_M_LOSS_ENTROPY_SCALED] = (double)ent_coef * -ent;
+    metrics[GS_M_KL] = tot[PM_KL] / B;
+    metrics[GS_M_APPROX_KL] = tot[PM_AKL] / B;
+    if (algo == ALGO_PPO) {
+        const double vl = tot[PM_VLOSS] / B;
+        metrics[GS_M_LOSS_VALUE] = vl;
+        metrics[GS_M_LOSS_VALUE_SCALED] = (double)vf_coef * vl;
+        metrics[GS_M_LOSS_TOTAL] = policy_loss + (double)vf_coef * vl + (double)ent_coef * -ent;
+        metrics[GS_M_CLIP_FRACTION] = tot[PM_CLIPF] / B;
+        metrics[GS_M_CLIP_FRACTION_VF] = tot[PM_CLIPF_VF] / B;
+        const double var_rv = (tot[PM_RV2] - tot[PM_RV] * tot[PM_RV] / B) / (B - 1.0);
+        const double var_r = (tot[PM_R2] - tot[PM_R] * tot[PM_R] / B) / (B - 1.0);
+        metrics[GS_M_EXPLAINED_VAR] = 1.0 - var_rv / var_r;
+    } else {
+        metrics[GS_M_LOSS_TOTAL] = policy_loss + (double)ent_coef * -ent;
+        metrics[GS_M_TARGETS_MEAN] = tot[PM_TGT] / B;
+        metrics[GS_M_TARGETS_STD] = ustd(tot[PM_TGT], tot[PM_TGT2], B);
+        if (normalize_ret) {
+            metrics[GS_M_RET_NORM_MEAN] = tot[PM_RETN] / B;
+            metrics[GS_M_RET_NORM_STD] = ustd(tot[PM_RETN], tot[PM_RETN2], B);
+        }
+    }
+    if (normalize_adv) {
+        metrics[GS_M_ADV_NORM_MEAN] = tot[PM_ADVN] / B;
+        metrics[GS_M_ADV_NORM_STD] = ustd(tot[PM_ADVN], tot[PM_ADVN2], B);
+    }
+    if (track) {
+        const double n0 = B * H1;
+        metrics[GS_M_ACT0_MEAN] = tot[PM_Z0] / n0;
+        metrics[GS_M_ACT0_STD] = ustd(tot[PM_Z0], tot[PM_Z0SQ], n0);
+        metrics[GS_M_ACT0_DEAD_PCT] = dead_stats[0] / n0;
+        metrics[GS_M_ACT0_DEAD_MAX] = dead_stats[1] / B;
+        if (H2 > 0) {
+            const double n1 = B * H2;
+            metrics[GS_M_ACT1_MEAN] = tot[PM_Z1] / n1;
+            metrics[GS_M_ACT1_STD] = ustd(tot[PM_Z1], tot[PM_Z1SQ], n1);
+            metrics[GS_M_ACT1_DEAD_PCT] = dead_stats[2] / n1;
+            metrics[GS_M_ACT1_DEAD_MAX] = dead_stats[3] / B;
+        }
+    }
+}
+
+// ---- minibatch moments of a rollout field (advantage / return batch normalisation) -------------------------------------
+__global__ void batch_moments_kernel(BatchDev b, const float* __restrict__ field, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double s = 0.0, s2 = 0.0;
+    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < b.n; pos += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)__ldg(field + sample_offset(b, pos));
+        s += v; s2 += v * v;
+    }
+    s = block_sum(s, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+        atomicAdd(out + 0, s);
+        atomicAdd(out + 1, s2);
+        if (blockIdx.x == 0) atomicAdd(out + 2, (double)b.n);
+    }
+}
+
+// ---- grad norms (all / backbone / policy_head / value_head) + global-norm clip -----------------------------------------
+__global__ void grad_norm_kernel(const float* __restrict__ g, ParamOffsets po, double* __restrict__ sq /* [3] zeroed */) {
+    __shared__ double scratch[32];
+    double part[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < po.total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)g[i];
+        const int grp = i < po.wp ? 0 : (i < po.wv ? 1 : 2);
+        part[grp] += v * v;
+    }
+    for (int k = 0; k < 3; ++k) {
+        const double v = block_sum(part[k], scratch);
+        if (threadIdx.x == 0 && v != 0.0) atomicAdd(sq + k, v);
+    }
+}
+
+__global__ void clip_scale_kernel(float* __restrict__ g, int64_t P, const double* __restrict__ sq, float max_norm,
+                                  double* __restrict__ metrics) {
+    const double total = sqrt(sq[0] + sq[1] + sq[2]);
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total + 1e-6), clamped to 1
+    double coef = 1.0;
+    if (max_norm > 0.f) { coef = (double)max_norm / (total + 1e-6); coef = coef > 1.0 ? 1.0 : coef; }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && metrics) {
+        metrics[GS_M_GRAD_NORM_ALL] = total;
+        metrics[GS_M_GRAD_NORM_BACKBONE] = sqrt(sq[0]);
+        metrics[GS_M_GRAD_NORM_POLICY] = sqrt(sq[1]);
+        metrics[GS_M_GRAD_NORM_VALUE] = sqrt(sq[2]);
+        metrics[GS_M_CLIP_COEF] = coef;
+    }
+    if (coef < 1.0) {
+        const float c = (float)coef;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) g[i] *= c;
+    }
+}
+
+// ---- Adam, single-tensor math of torch.optim.Adam (no amsgrad / weight decay / maximize) ---------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, int64_t* __restrict__ step_count, float lr, float beta1, float beta2, float eps) {
+    const int64_t step = *step_count + 1;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+__global__ void adam_bump_kernel(int64_t* step_count) { *step_count += 1; }
+
+// ---- host launchers ----------------------------------------------------------------------------------------------------
+static MlpDev to_dev(const gs_mlp_t* m) {
+    MlpDev d;
+    d.D = m->obs_dim; d.H1 = m->hidden1; d.H2 = m->hidden2; d.A = m->n_actions; d.has_value = m->has_value; d.act = m->activation;
+    d.w1 = m->w1; d.b1 = m->b1; d.w2 = m->w2; d.b2 = m->b2; d.wp = m->wp; d.bp = m->bp; d.wv = m->wv; d.bv = m->bv;
+    return d;
+}
+
+int validate_mlp(const gs_mlp_t* m) {
+    if (!m) GS_FAIL("mlp is NULL");
+    if (m->obs_dim < 1 || m->obs_dim > kDP) GS_FAIL("obs_dim %d unsupported (1..%d)", m->obs_dim, kDP);
+    if (m->n_actions < 2 || m->n_actions + (m->has_value ? 1 : 0) > kNH) GS_FAIL("n_actions %d unsupported (2..3)", m->n_actions);
+    const int h1 = m->hidden1, h2 = m->hidden2;
+    const bool ok = (h1 == 64 && h2 == 0) || (h1 == 64 && h2 == 64) || (h1 == 128 && h2 == 128) || (h1 == 256 && h2 == 256);
+    if (!ok) GS_FAIL("hidden dims (%d,%d) unsupported by the engine: (64,), (64,64), (128,128), (256,256)", h1, h2);
+    if (m->activation != GS_ACT_RELU && m->activation != GS_ACT_TANH) GS_FAIL("activation %d unsupported", m->activation);
+    if (!m->w1 || !m->b1 || !m->wp || !m->bp || (h2 > 0 && (!m->w2 || !m->b2)) || (m->has_value && (!m->wv || !m->bv)))
+        GS_FAIL("mlp has NULL weight pointers");
+    return 0;
+}
+
+struct UpdateWs {  // workspace carve-up
+    float* grad_partials;
+    double* metric_partials;
+    uint32_t* dead;
+    double* sq;
+};
+
+static int update_grid(int device) { return 2 * sm_count(device); }
+
+static int64_t ws_bytes(const gs_mlp_t* m, int device) {
+    const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
+    const int grid = update_grid(device);
+    int64_t b = 0;
+    b += ((int64_t)grid * P * 4 + 255) / 256 * 256;
+    b += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
+    b += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
+    b += 256;
+    return b;
+}
+
+static UpdateWs carve(void* ws, const gs_mlp_t* m, int grid) {
+    const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
+    char* p = (char*)ws;
+    UpdateWs w;
+    w.grad_partials = (float*)p; p += ((int64_t)grid * P * 4 + 255) / 256 * 256;
+    w.metric_partials = (double*)p; p += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
+    w.dead = (uint32_t*)p; p += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
+    w.sq = (double*)p;
+    return w;
+}
+
+template <class C, int ALGO>
+static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom,
+                             const double* ret_mom, float* grads_flat, double* metrics, void* ws, int device, cudaStream_t st) {
+    const int grid_max = update_grid(device);
+    const int64_t n_tiles = (b.n + C::S - 1) / C::S;
+    const int grid = (int)(n_tiles < grid_max ? n_tiles : grid_max);
+    const UpdateWs w = carve(ws, m, grid_max);
+    const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
+    const size_t smem = (size_t)C::kSmemFloats * sizeof(float);
+    const MlpDev md = to_dev(m);
+    if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)(m->hidden1 + m->hidden2) * 4, st));
+    if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
+    auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(md, b, hp, adv_mom, ret_mom, w.grad_partials, grads_flat, w.metric_partials, w.dead);
+    GS_LAUNCH_CHECK();
+    if (C::kPersist) {
+        reduce_partials_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.grad_partials, grid, P, grads_flat);
+        GS_LAUNCH_CHECK();
+    }
+    finalize_metrics_kernel<<<1, 64, 0, st>>>(w.metric_partials, grid, ALGO, m->hidden1, m->hidden2, track ? 1 : 0, hp.vf_coef,
+                                              hp.ent_coef, hp.normalize_adv, hp.normalize_ret, w.dead, metrics);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int ALGO>
+static int launch_update(const gs_mlp_t* m, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom,
+                         const double* ret_mom, float* grads_flat, double* metrics, void* ws, int64_t ws_size, cudaStream_t st) {
+    if (validate_mlp(m)) return -1;
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    if (ws_size < ws_bytes(m, device)) GS_FAIL("workspace too small: %lld < %lld", (long long)ws_size, (long long)ws_bytes(m, device));
+    if (b.n <= 0) GS_FAIL("empty minibatch");
+    if (b.D != m->obs_dim) GS_FAIL("batch obs_dim %d != mlp obs_dim %d", b.D, m->obs_dim);
+    const int h1 = m->hidden1, h2 = m->hidden2;
+#define GS_DISPATCH(H1, H2, S) \
+    return launch_update_cfg<TileCfg<H1, H2, S>, ALGO>(m, b, hp, track, adv_mom, ret_mom, grads_flat, metrics, ws, device, st)
+    if (h1 == 64 && h2 == 64) GS_DISPATCH(64, 64, 128);
+    if (h1 == 64 && h2 == 0) GS_DISPATCH(64, 0, 128);
+    if (h1 == 128 && h2 == 128) GS_DISPATCH(128, 128, 64);
+    if (h1 == 256 && h2 == 256) GS_DISPATCH(256, 256, 64);
+#undef GS_DISPATCH
+    GS_FAIL("no kernel for hidden dims (%d,%d)", h1, h2);
+}
+
+static BatchDev to_dev(const gs_batch_t* b) {
+    BatchDev d;
+    d.n = b->n; d.idx = b->idx; d.perm_key = b->perm_key; d.perm_offset = b->perm_offset; d.perm_len = b->perm_len;
+    d.idx_map = b->idx_map; d.T = b->T; d.D = b->obs_dim; d.N = b->N; d.obs = b->obs; d.actions = b->actions;
+    d.logp_old = b->logp_old; d.values_old = b->values_old; d.adv = b->adv; d.ret = b->ret;
+    return d;
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" {
+
+int64_t gs_mlp_param_count(const gs_mlp_t* m) {
+    if (validate_mlp(m)) return -1;
+    return mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
+}
+
+int64_t gs_update_workspace_bytes(const gs_mlp_t* m, int device) {
+    if (validate_mlp(m)) return -1;
+    return ws_bytes(m, device);
+}
+
+int gs_batch_moments(const gs_batch_t* batch, const float* field, double* out, void* stream) {
+    if (!batch || !field || !out) GS_FAIL("gs_batch_moments: NULL argument");
+    if (batch->n <= 0) GS_FAIL("empty minibatch");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    const BatchDev b = to_dev(batch);
+    int64_t blocks = (b.n + 255) / 256;
+    const int cap = 4 * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    batch_moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, field, out);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_ppo_step(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_ppo_hparams_t* hp, const double* adv_moments,
+                float* grads_flat, double* metrics, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!mlp || !batch || !hp || !grads_flat || !metrics || !workspace) GS_FAIL("gs_ppo_step: NULL argument");
+    if (!mlp->has_value) GS_FAIL("PPO requires a policy with a value head");  // agents/ppo/ppo_agent.py:41-44
+    if (hp->normalize_adv && !adv_moments) GS_FAIL("normalize_adv needs adv_moments");
+    if (!batch->values_old || !batch->adv || !batch->ret || !batch->logp_old || !batch->actions || !batch->obs)
+        GS_FAIL("gs_ppo_step: batch has NULL arrays");
+    HpDev h;
+    h.clip_lo = (float)(1.0 - (double)hp->clip_range);
+    h.clip_hi = (float)(1.0 + (double)hp->clip_range);
+    h.clip_vf = hp->clip_range_vf; h.vf_coef = hp->vf_coef; h.ent_coef = hp->ent_coef;
+    h.normalize_adv = hp->normalize_adv; h.normalize_ret = 0; h.policy_targets = 1;
+    return launch_update<ALGO_PPO>(mlp, to_dev(batch), h, hp->track_activations != 0, adv_moments, nullptr, grads_flat, metrics,
+                                   workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gs_reinforce_step(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_reinforce_hparams_t* hp, const double* ret_moments,
+                      const double* adv_moments, float* grads_flat, double* metrics, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+    if (!mlp || !batch || !hp || !grads_flat || !metrics || !workspace) GS_FAIL("gs_reinforce_step: NULL argument");
+    if (hp->normalize_adv && !adv_moments) GS_FAIL("normalize_adv needs adv_moments");
+    if (hp->normalize_returns && !ret_moments) GS_FAIL("normalize_returns needs ret_moments");
+    if (hp->policy_targets != 0 && hp->policy_targets != 1) GS_FAIL("Invalid policy targets: %d", hp->policy_targets);
+    if (!batch->adv || !batch->ret || !batch->logp_old || !batch->actions || !batch->obs) GS_FAIL("gs_reinforce_step: batch has NULL arrays");
+    HpDev h;
+    h.clip_lo = h.clip_hi = h.clip_vf = h.vf_coef = 0.f;
+    h.ent_coef = hp->ent_coef;
+    h.normalize_adv = hp->normalize_adv; h.normalize_ret = hp->normalize_returns; h.policy_targets = hp->policy_targets;
+    return launch_update<ALGO_REINFORCE>(mlp, to_dev(batch), h, hp->track_activations != 0, adv_moments, ret_moments, grads_flat,
+                                         metrics, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gs_clip_grad_norm(const gs_mlp_t* mlp, float* grads_flat, float max_norm, double* metrics, void* stream) {
+    if (validate_mlp(mlp)) return -1;
+    if (!grads_flat || !metrics) GS_FAIL("gs_clip_grad_norm: NULL argument");
+    const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sq = metrics + GS_M_SCRATCH;  // squared norms of [backbone, policy_head, value_head]
+    GS_CUDA(cudaMemsetAsync(sq, 0, 3 * sizeof(double), st));
+    const int blocks = (int)((po.total + 1023) / 1024 < 64 ? (po.total + 1023) / 1024 : 64);
+    grad_norm_kernel<<<blocks, 256, 0, st>>>(grads_flat, po, sq);
+    GS_LAUNCH_CHECK();
+    clip_scale_kernel<<<blocks, 256, 0, st>>>(grads_flat, po.total, sq, max_norm, metrics);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_count,
+                 float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!params_flat || !grads_flat || !exp_avg || !exp_avg_sq || !step_count || n <= 0) GS_FAIL("gs_adam_step: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)((n + 255) / 256 < 296 ? (n + 255) / 256 : 296);
+    adam_kernel<<<blocks, 256, 0, st>>>(params_flat, grads_flat, exp_avg, exp_avg_sq, n, step_count, lr, beta1, beta2, eps);
+    GS_LAUNCH_CHECK();
+    adam_bump_kernel<<<1, 1, 0, st>>>(step_count);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -75,7 +75,11 @@ enum {
     GS_M_GRAD_NORM_POLICY,    /* opt/grads/norm/policy_head */
     GS_M_GRAD_NORM_VALUE,     /* opt/grads/norm/value_head  */
     GS_M_CLIP_COEF,           /* scale applied by the global-norm clip */
-    GS_N_METRICS = 32
+    GS_M_RET_NORM_MEAN,       /* roll/return/norm/mean (REINFORCE, normalize_returns == batch) */
+    GS_M_RET_NORM_STD,        /* roll/return/norm/std  */
+    GS_M_BATCH_COUNT,         /* samples that contributed */
+    GS_M_SCRATCH = 32,        /* [32..39] device scratch of gs_clip_grad_norm; not a metric */
+    GS_N_METRICS = 40
 };
 
 typedef struct gs_env gs_env_t; /* opaque: SoA fp64 state, elapsed steps, episode accumulators, RNG key, wrapper tables */
@@ -207,13 +211,14 @@ int gs_rollout_collect(gs_env_t* env, const gs_mlp_t* mlp, const gs_rollout_t* b
 /* compute_batched_gae_advantages_and_returns :115-155 (fp32 arithmetic, reverse scan over t) */
 int gs_gae(const float* values, const float* rewards, const uint8_t* dones, const uint8_t* timeouts,
            const float* last_values, const float* bootstrapped /* nullable (T,N) */, int T, int64_t N,
-           float gamma, float gae_lambda, float* adv, float* ret, void* stream);
+           double gamma, double gae_lambda /* Python floats of the reference, rounded to fp32 exactly as numpy does */,
+           float* adv, float* ret, void* stream);
 /* compute_batched_mc_returns :67-91 (+ convert_returns_to_full_episode :93-113 when episode_mode).
  * timeouts nullable == all False (mc_treat_timeouts_as_terminals, rollout_collector.py:392-393).
  * last_terminal (nullable, (N,) int32): index of the last real terminal per env, -1 if none —
  * the per-env fact behind _build_valid_mask_and_index_map :33-52. */
 int gs_mc_returns(const float* rewards, const uint8_t* dones, const uint8_t* timeouts, int T, int64_t N,
-                  float gamma, int episode_mode, float* ret, int32_t* last_terminal, void* stream);
+                  double gamma, int episode_mode, float* ret, int32_t* last_terminal, void* stream);
 /* _build_valid_mask_and_index_map :33-52 + _build_idx_map_from_valid_mask :19-30, env-major (N*T,).
  * n_valid (device int64[1]) receives the number of valid entries (0 => reference returns None). */
 int gs_valid_index_map(const int32_t* last_terminal, int T, int64_t N, uint8_t* valid_mask, int64_t* idx_map,
@@ -224,7 +229,7 @@ int64_t gs_valid_index_map_workspace_bytes(int64_t N);
  * Accumulates INTO out (caller zeroes). */
 int gs_moments(const float* x, const int32_t* last_terminal, int T, int64_t N, double* out, void* stream);
 /* y = (x - mean)/(std + eps) with mean/std derived on device from moments (population std, numpy semantics,
- * returns_advantages.py:55-64) or y = x - moments-mean*0 - shift when eps < 0 is not used; see gs_shift. */
+ * returns_advantages.py:55-64); in place allowed. */
 int gs_normalize(const float* x, int64_t n, const double* moments, float eps, float* y, void* stream);
 /* y = x - mean(moments)  (MC baseline, rollout_collector.py:423-425) */
 int gs_shift_by_mean(const float* x, int64_t n, const double* moments, float* y, void* stream);

@@ -1,0 +1,114 @@
+"""GPU parity: device vector envs vs the fp64 CPU restatement (oracle/envs.c) on identical Philox reset streams and
+identical action sequences.  Bars (BASELINE.json north_star): observations within 1e-6, termination / truncation
+flags and episode lengths bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import envs as OE
+
+pytestmark = pytest.mark.gpu
+
+ENVS = ["CartPole-v1", "Acrobot-v1", "MountainCar-v0"]
+
+
+def _rollout_pair(env_id, n, steps, seed, max_episode_steps=None, wrappers=(), rng_seed=0, env_id_offset=0):
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    dev_wr = []
+    for spec in wrappers:
+        k, p = OE.wrapper_params(spec)
+        assert N.WRAPPER_KINDS[spec["id"]] == k
+        dev_wr.append((k, list(p)))
+    o = OE.OracleVecEnv(env_id, n, seed=seed, max_episode_steps=max_episode_steps, env_wrappers=list(wrappers), env_id_offset=env_id_offset)
+    g = E.DevEnv(env_id, n, seed=seed, max_episode_steps=max_episode_steps or 0, wrappers=dev_wr, env_id_offset=env_id_offset)
+    obs_o, _ = o.reset()
+    obs_g = g.reset()
+    np.testing.assert_array_equal(obs_g, obs_o)  # Philox + IEEE affine map: bit-exact
+    rng = np.random.default_rng(rng_seed)
+    nA = OE.N_ACTIONS[o.kind]
+    n_done = 0
+    for t in range(steps):
+        a = rng.integers(0, nA, n).astype(np.int32)
+        oo, ro, to, tro, info = o.step(a)
+        og, rg, tg, trg, epr, epl = g.step(a)
+        np.testing.assert_allclose(og, oo, rtol=0, atol=1e-6, err_msg=f"obs step {t}")
+        np.testing.assert_array_equal(tg, to, err_msg=f"terminated step {t}")
+        np.testing.assert_array_equal(trg, tro, err_msg=f"truncated step {t}")
+        np.testing.assert_allclose(rg, ro.astype(np.float32), rtol=1e-6, atol=1e-7, err_msg=f"reward step {t}")
+        done = to | tro
+        if done.any():
+            n_done += int(done.sum())
+            np.testing.assert_array_equal(epl[done], info["episode"]["l"][done], err_msg=f"episode length step {t}")
+            np.testing.assert_allclose(epr[done], info["episode"]["r"][done], rtol=1e-9, err_msg=f"episode return step {t}")
+        assert (epl[~done] == 0).all()
+    so, eo = o.get_state()
+    sg, eg = g.get_state()
+    np.testing.assert_allclose(sg, so, rtol=1e-9, atol=1e-9)
+    np.testing.assert_array_equal(eg, eo)
+    return n_done
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_trajectories_match_oracle(env_id):
+    steps = {"CartPole-v1": 200, "Acrobot-v1": 120, "MountainCar-v0": 420}[env_id]
+    n_done = _rollout_pair(env_id, 300, steps, seed=42)
+    assert n_done > 0  # autoreset / TimeLimit path exercised (CartPole terminates, MountainCar truncates at 200)
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_timelimit_truncation_and_autoreset(env_id):
+    n_done = _rollout_pair(env_id, 65, 40, seed=7, max_episode_steps=6)
+    assert n_done >= 65 * 5
+
+
+def test_env_shards_reproduce_global_streams():
+    """Rank r owning envs [r*N/W, ...) sees the same streams as the unsharded run."""
+    import engine_api as E
+
+    full = E.DevEnv("CartPole-v1", 64, seed=9)
+    shard = E.DevEnv("CartPole-v1", 16, seed=9, env_id_offset=48)
+    np.testing.assert_array_equal(full.reset()[48:], shard.reset())
+    _rollout_pair("CartPole-v1", 16, 60, seed=9, env_id_offset=48)
+
+
+def test_env_set_state_single_step_known_answers():
+    import engine_api as E
+
+    g = E.DevEnv("CartPole-v1", 2)
+    g.reset()
+    g.set_state(np.zeros((4, 2)), np.zeros(2, np.int32))
+    obs, r, term, trunc, _, _ = g.step([1, 0])
+    temp = 10.0 / 1.1
+    thetaacc = (-temp) / (0.5 * (4.0 / 3.0 - 0.1 / 1.1))
+    xacc = temp - 0.05 * thetaacc / 1.1
+    s, el = g.get_state()
+    np.testing.assert_allclose(s[:, 0], [0.0, 0.02 * xacc, 0.0, 0.02 * thetaacc], rtol=1e-15)
+    np.testing.assert_allclose(s[:, 1], [0.0, -0.02 * xacc, 0.0, -0.02 * thetaacc], rtol=1e-15)
+    assert (r == 1.0).all() and not term.any() and not trunc.any() and (el == 1).all()
+
+
+@pytest.mark.parametrize("spec", [
+    dict(id="MountainCarV0_StateCountBonus", position_bins=50, velocity_bins=50, bonus_scale=0.1, bonus_type="count"),
+    dict(id="MountainCarV0_StateCountBonus", position_bins=10, velocity_bins=7, bonus_scale=1.0, bonus_type="inverse", min_count=2),
+    dict(id="MountainCarV0_StateCountBonus", position_bins=20, velocity_bins=20, bonus_scale=0.5, bonus_type="log"),
+    dict(id="MountainCarV0_RewardShaper", position_reward_scale=100.0, velocity_reward_scale=10.0, height_reward_scale=50.0),
+])
+def test_mountaincar_wrappers_match_oracle(spec):
+    _rollout_pair("MountainCar-v0", 130, 260, seed=3, wrappers=[spec])
+
+
+def test_cartpole_reward_shaper_matches_oracle():
+    spec = dict(id="CartPoleV1_RewardShaper", angle_reward_scale=1.0, position_reward_scale=0.25, clip_potential=True)
+    _rollout_pair("CartPole-v1", 130, 150, seed=11, wrappers=[spec])
+
+
+def test_wrapper_errors_fail_loudly():
+    import ctypes as C
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    g = E.DevEnv("CartPole-v1", 4)
+    arr = (C.c_double * 5)(50, 50, 0.1, 0, 1)
+    assert N.lib().gs_wrapper_attach(g.h, 1, arr, 5) != 0  # MountainCar wrapper on CartPole
+    assert b"does not apply" in N.lib().gs_last_error()

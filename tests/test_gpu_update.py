@@ -1,0 +1,233 @@
+"""GPU parity: gs_ppo_step / gs_reinforce_step / gs_clip_grad_norm / gs_adam_step vs the torch autograd oracle and the
+fixtures produced by the reference's PPOAgent / REINFORCEAgent.  Bar: loss and gradients within 1e-4 (relative to the
+gradient scale), metrics within 1e-4."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import policy as P
+
+pytestmark = pytest.mark.gpu
+
+TAGS = ["cartpole64", "acrobot128", "mcar256", "tiny64"]
+PPO_METRICS = ["opt/loss/total", "opt/loss/policy", "opt/loss/entropy", "opt/policy/entropy", "opt/loss/entropy_scaled",
+               "opt/loss/value", "opt/loss/value_scaled", "opt/ppo/clip_fraction", "opt/ppo/clip_fraction_vf",
+               "opt/value/explained_var", "opt/ppo/kl", "opt/ppo/approx_kl"]
+
+
+def _params(d, prefix):
+    return {k: torch.from_numpy(d[prefix + k]) for k in P.PARAM_ORDER if prefix + k in d.files}
+
+
+def _assert_grads_close(g, ref, tol=1e-4):
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(g, ref, rtol=tol, atol=tol * scale)
+
+
+def _ppo_hp(N, clip=0.2, clip_vf=0.2, vf=0.5, ent=0.01, norm=True, track=True):
+    hp = N.GsPpoHparams()
+    hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef = clip, clip_vf, vf, ent
+    hp.normalize_adv, hp.track_activations = int(norm), int(track)
+    return hp
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("norm", ["batch", "off"])
+def test_ppo_step_matches_reference_fixture(golden_dir, tag, norm):
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    d = np.load(os.path.join(golden_dir, f"policy_{tag}.npz"))
+    p = _params(d, "p_")
+    B = d["obs"].shape[0]
+    batch, keep = E.make_batch(1, B, E.cu(d["obs"][None]), E.cu(d["actions"][None].astype(np.int32)), E.cu(d["old_logp"][None]),
+                               E.cu(d["values_old"][None]), E.cu(d["adv"][None]), E.cu(d["ret"][None]))
+    g_raw, g_clip, m = E.update_step("ppo", E.dev_params(p), batch, _ppo_hp(N, norm=(norm == "batch")), max_norm=0.5)
+    ref = np.concatenate([d[f"ppo_{norm}_g_{k}"].ravel() for k in P.PARAM_ORDER if f"ppo_{norm}_g_{k}" in d.files])
+    _assert_grads_close(g_raw, ref)
+    np.testing.assert_allclose(m["opt/loss/total"], float(d[f"ppo_{norm}_loss"]), rtol=1e-4, atol=1e-6)
+    for k in PPO_METRICS:
+        np.testing.assert_allclose(m[k], float(d[f"ppo_{norm}_m_{k}"]), rtol=1e-4, atol=2e-6, err_msg=k)
+    if norm == "batch":
+        np.testing.assert_allclose(m["roll/adv/norm/mean"], float(d[f"ppo_{norm}_m_roll/adv/norm/mean"]), atol=1e-6)
+        np.testing.assert_allclose(m["roll/adv/norm/std"], float(d[f"ppo_{norm}_m_roll/adv/norm/std"]), rtol=1e-4)
+    for layer in ("backbone.0", "backbone.2"):
+        if f"ppo_{norm}_m_opt/activations/{layer}/mean" not in d.files:
+            continue
+        for stat, tol in (("mean", 1e-4), ("std", 1e-4), ("dead_pct", 1e-6), ("dead_max", 1e-6)):
+            np.testing.assert_allclose(m[f"opt/activations/{layer}/{stat}"], float(d[f"ppo_{norm}_m_opt/activations/{layer}/{stat}"]),
+                                       rtol=tol, atol=1e-6, err_msg=f"{layer}/{stat}")
+    for grp in ("all", "backbone", "policy_head", "value_head"):
+        np.testing.assert_allclose(m[f"opt/grads/norm/{grp}"], float(d[f"ppo_{norm}_m_opt/grads/norm/{grp}"]), rtol=1e-4)
+    ref_clip = np.concatenate([d[f"ppo_{norm}_gc_{k}"].ravel() for k in P.PARAM_ORDER if f"ppo_{norm}_gc_{k}" in d.files])
+    _assert_grads_close(g_clip, ref_clip)
+
+
+@pytest.mark.parametrize("D,hidden,A", [(4, (64, 64), 2), (6, (128, 128), 3), (2, (256, 256), 3), (4, (64,), 2)])
+@pytest.mark.parametrize("mode", ["idx", "identity", "idx_map"])
+@pytest.mark.parametrize("activation", ["relu", "tanh"])
+def test_ppo_step_gather_modes_vs_oracle(D, hidden, A, mode, activation):
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    T, Nn = 9, 61
+    g = torch.Generator().manual_seed(T * Nn + D)
+    p = P.random_params(D, hidden, A, seed=D)
+    obs = torch.randn(T, Nn, D, generator=g)
+    actions = torch.randint(0, A, (T, Nn), generator=g)
+    with torch.no_grad():
+        logits, v = P.forward(p, obs.reshape(-1, D), activation)
+        lp_all = logits - logits.logsumexp(-1, keepdim=True)
+    old_logp = (lp_all.gather(-1, actions.reshape(-1, 1)).squeeze(-1) + 0.2 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    values_old = (v + 0.3 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    adv = torch.randn(T, Nn, generator=g) * 2 + 0.3
+    ret = values_old + adv
+    total = T * Nn
+    idx_map = None
+    if mode == "idx":
+        ids = torch.randint(0, total, (300,), generator=g).numpy()
+        src = ids
+        batch, keep = E.make_batch(T, Nn, E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret), idx=ids)
+    elif mode == "identity":
+        src = np.arange(100, 400)
+        batch, keep = E.make_batch(T, Nn, E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret),
+                                   n=300, perm_offset=100)
+    else:
+        ids = torch.randint(0, total, (257,), generator=g).numpy()
+        idx_map = torch.randint(0, total, (total,), generator=g).numpy()
+        src = idx_map[ids]
+        batch, keep = E.make_batch(T, Nn, E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret),
+                                   idx=ids, idx_map=idx_map)
+    e, t = src // T, src % T   # env-major sample id -> (env, step)
+    sel = lambda x: x[t, e]
+    hp = _ppo_hp(N, clip=0.15, clip_vf=0.25, vf=0.7, ent=0.02)
+    g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, hp, activation=activation)
+    loss, flat, om = P.loss_and_grads(P.ppo_loss, p, sel(obs), sel(actions), sel(old_logp), sel(values_old), sel(adv), sel(ret),
+                                      clip_range=0.15, clip_range_vf=0.25, vf_coef=0.7, ent_coef=0.02, normalize_adv=True, activation=activation)
+    _assert_grads_close(g_raw, flat.numpy())
+    np.testing.assert_allclose(m["opt/loss/total"], float(loss), rtol=1e-4, atol=1e-6)
+    for k in PPO_METRICS:
+        np.testing.assert_allclose(m[k], float(om[k]), rtol=1e-4, atol=2e-6, err_msg=k)
+    assert m["opt/batch_count"] == len(src)
+
+
+def test_ppo_step_full_size_minibatch_vs_oracle():
+    """A C2-sized minibatch (1,048,576 samples gathered from a 128 x 65,536 rollout by the device permutation)."""
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    T, Nn, D, A = 128, 65536, 4, 2
+    g = torch.Generator().manual_seed(0)
+    p = P.random_params(D, (64, 64), A, seed=1)
+    obs = torch.randn(T, Nn, D, generator=g) * 0.5
+    actions = torch.randint(0, A, (T, Nn), generator=g)
+    with torch.no_grad():
+        logits, v = P.forward(p, obs.reshape(-1, D))
+        lp_all = logits - logits.logsumexp(-1, keepdim=True)
+    old_logp = (lp_all.gather(-1, actions.reshape(-1, 1)).squeeze(-1) + 0.1 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    values_old = (v + 0.3 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    adv = torch.randn(T, Nn, generator=g)
+    ret = values_old + adv
+    total, B = T * Nn, 1 << 20
+    dev = [E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret)]
+    # the device permutation is a bijection of [0, total): minibatch k of an epoch covers disjoint ids
+    ids = []
+    import gymnasium_solver_b200.utils.samplers as S
+    perm = S.feistel_permutation(total, key=77, device="cuda")
+    assert torch.equal(torch.sort(perm).values, torch.arange(total, device="cuda"))
+    src = perm[3 * B:4 * B].cpu().numpy()
+    batch, keep = E.make_batch(T, Nn, *dev, n=B, perm_key=77, perm_offset=3 * B, perm_len=total)
+    hp = _ppo_hp(N, track=False)
+    g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, hp)
+    e, t = src // T, src % T
+    sel = lambda x: x[t, e]
+    loss, flat, om = P.loss_and_grads(P.ppo_loss, {k: v_.double() for k, v_ in p.items()}, sel(obs).double(), sel(actions), sel(old_logp).double(),
+                                      sel(values_old).double(), sel(adv).double(), sel(ret).double(), clip_range=0.2, clip_range_vf=0.2,
+                                      vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
+    _assert_grads_close(g_raw, flat.numpy())
+    np.testing.assert_allclose(m["opt/loss/total"], float(loss), rtol=1e-4)
+    for k in PPO_METRICS:
+        np.testing.assert_allclose(m[k], float(om[k]), rtol=2e-4, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("cfg", [("returns", "off", "off"), ("advantages", "off", "batch"), ("returns", "batch", "off")])
+def test_reinforce_step_matches_reference_fixture(golden_dir, tag, cfg):
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    targets, nr, na = cfg
+    d = np.load(os.path.join(golden_dir, f"policy_{tag}.npz"))
+    p = _params(d, "rp_")
+    B = d["obs"].shape[0]
+    batch, keep = E.make_batch(1, B, E.cu(d["obs"][None]), E.cu(d["actions"][None].astype(np.int32)), E.cu(d["r_old_logp"][None]),
+                               E.cu(d["values_old"][None]), E.cu(d["adv"][None]), E.cu(d["ret"][None]))
+    hp = N.GsReinforceHparams()
+    hp.ent_coef, hp.policy_targets = 0.01, 0 if targets == "returns" else 1
+    hp.normalize_returns, hp.normalize_adv, hp.track_activations = int(nr == "batch"), int(na == "batch"), 0
+    g_raw, _, m = E.update_step("reinforce", E.dev_params(p), batch, hp)
+    key = f"rf_{targets}_{nr}_{na}"
+    ref = np.concatenate([d[f"{key}_g_{k}"].ravel() for k in P.PARAM_ORDER if f"{key}_g_{k}" in d.files])
+    _assert_grads_close(g_raw, ref)
+    for k in ("opt/loss/total", "opt/loss/policy", "opt/policy/entropy", "opt/ppo/kl", "opt/ppo/approx_kl", "policy_targets_mean", "policy_targets_std"):
+        np.testing.assert_allclose(m[k], float(d[f"{key}_m_{k}"]), rtol=1e-4, atol=2e-6, err_msg=k)
+
+
+def test_ppo_clip_math_reference_kat():
+    """reference tests/test_ppo.py:52-107 — one ratio above 1+clip with adv > 0, one below 1-clip with adv < 0: the
+    clipped branch is selected for both, so the policy gradient vanishes and loss == -(1.5*1.2 - 2.0*0.8)/2."""
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    p = P.random_params(4, (64, 64), 2, seed=5)
+    obs = torch.randn(2, 4, generator=torch.Generator().manual_seed(1))
+    actions = torch.tensor([0, 1])
+    with torch.no_grad():
+        logits, v = P.forward(p, obs)
+        lp = (logits - logits.logsumexp(-1, keepdim=True)).gather(-1, actions[:, None]).squeeze(-1)
+    ratios = torch.tensor([1.5, 0.55])
+    old_logp = lp - torch.log(ratios)
+    adv = torch.tensor([1.5, -2.0])
+    batch, keep = E.make_batch(1, 2, E.cu(obs[None]), E.cu(actions[None].int()), E.cu(old_logp[None]), E.cu(v[None]), E.cu(adv[None]), E.cu(v[None]))
+    hp = _ppo_hp(N, clip=0.2, clip_vf=1e6, vf=0.0, ent=0.0, norm=False, track=False)
+    g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, hp)
+    np.testing.assert_allclose(m["opt/loss/total"], -(1.5 * 1.2 + -2.0 * 0.8) / 2, rtol=1e-5)
+    assert m["opt/ppo/clip_fraction"] == 1.0
+    np.testing.assert_allclose(g_raw, 0.0, atol=1e-7)
+
+
+def test_adam_step_matches_torch():
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    n = 4675
+    g = torch.Generator().manual_seed(2)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = E.cu(p0.clone())
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(5):
+        grad = torch.randn(n, generator=g) * (0.1 + it)
+        ref.grad = grad.clone()
+        opt.step()
+        gd = E.cu(grad)
+        N.check(N.lib().gs_adam_step(N.ptr(p), N.ptr(gd), N.ptr(m), N.ptr(v), n, N.ptr(step), 1e-3, 0.9, 0.999, 1e-8, N.stream()))
+    E.sync()
+    assert int(step.item()) == 5
+    np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_update_errors_fail_loudly():
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    p = P.random_params(4, (64, 64), 2, has_value=False)
+    z = torch.zeros(1, 4)
+    batch, keep = E.make_batch(1, 4, E.cu(torch.zeros(1, 4, 4)), E.cu(z.int()), E.cu(z), E.cu(z), E.cu(z), E.cu(z))
+    with pytest.raises(N.EngineError, match="value head"):
+        E.update_step("ppo", E.dev_params(p), batch, _ppo_hp(N))
