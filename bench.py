@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Headline benchmark: PPO env-steps/sec (collect + GAE + update) on CartPole-v1, BASELINE.json config C2
+(65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP, PPO defaults: 10 passes, 8 minibatches per pass).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one training iteration over one rollout: fused collect (128 vector steps of 65,536 envs), GAE, then
+n_epochs x n_minibatches fused forward/loss/backward kernels each followed by the gradient all-reduce (N > 1), global-norm
+clip and the torch Adam step.  Weak scaling: every rank owns 65,536 envs.  Rank 0 prints ONE JSON line.
+
+`value`   device-timed, no host round trips inside the timed region (inputs — env state, weights — resident in HBM).
+`e2e`     the same iteration through the public API (agent.train_one_rollout + metrics) with, every step, the
+          hyper-parameter block copied host->device from pinned memory and the epoch metrics, episode statistics and a
+          weight snapshot copied device->host into pinned memory, then a host synchronisation.
+`--impl reference`  the reference's CPU path restated by oracle/ (C env step loop + torch CPU policy + numpy GAE + torch
+          autograd PPO loss + clip + Adam) on all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_PASS = {(64, 64): 27264, (256, 256): 403968}   # 3 x forward flops
+GAE_BYTES_PER_ELEM = 22                                           # 18 B/elem + 4 B/elem dense bootstrapped array
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons = index, period, [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"} \
+            if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else \
+            {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+             nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------------- b200 arm
+def build_agent_for_bench(args, rank, world):
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.config import load_config
+
+    cfg = load_config("CartPole-v1", "ppo_b200")
+    cfg.n_envs = args.n_envs * world
+    cfg.n_steps = args.n_steps
+    cfg.batch_size = args.batch_size * world
+    cfg.n_epochs = args.n_epochs
+    cfg.model_id = args.model_id
+    from gymnasium_solver_b200.utils.model_registry import resolve_model_spec
+    cfg._hidden_dims = resolve_model_spec(args.model_id).hidden_dims
+    cfg.eval_freq_epochs = None
+    cfg.max_env_steps = None
+    cfg.track_activations = bool(args.track_activations)
+    cfg.validate()
+    return build_agent(cfg, rank=rank, world_size=world), cfg
+
+
+def launches_per_step(cfg, world):
+    """Engine kernels launched per training iteration (ours; torch's optimizer / bookkeeping kernels are not counted)."""
+    n_mb = (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs)
+    per_rollout = 1 + 2 + 1 + 2          # collect, obs/reward moments, gae, adv/ret moments
+    per_mb = 1 + 1 + 1 + 1 + 2           # batch_moments, update, reduce_partials, finalize_metrics, grad_norm + clip_scale
+    return per_rollout + n_mb * per_mb
+
+
+def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dist = torch.distributed
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    agent, cfg = build_agent_for_bench(args, rank, world)
+    col = agent.get_rollout_collector("train")
+    steps_per_iter_local = agent.local_n_envs * int(cfg.n_steps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also first-touch of every buffer) ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        agent.train_one_rollout()
+    agent.pop_epoch_metrics()
+    barrier()
+
+    # ---- timed region: device time, no host round trips ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        agent.train_one_rollout()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = steps_per_iter_local * world * args.steps / (ms_total * 1e-3)
+    agent.pop_epoch_metrics()
+
+    # ---- e2e: public API + per-step H2D of the hyper-parameter block and D2H of metrics / episode stats / weights ------
+    hp_host = torch.tensor([cfg.policy_lr, cfg.clip_range, cfg.clip_range_vf, cfg.vf_coef, cfg.ent_coef, 0, 0, 0],
+                           dtype=torch.float32).pin_memory()
+    hp_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+    P = agent.policy_model.flat_params.numel()
+    weights_host = torch.empty(P, dtype=torch.float32).pin_memory()
+    metrics_host = torch.empty(40, dtype=torch.float64).pin_memory()
+    h2d_bytes = hp_host.numel() * 4
+    d2h_bytes = P * 4 + 40 * 8 + 18 * 8          # weights + metric vector + collector running stats (6x3 doubles)
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        hp_host[5] = float(i)
+        hp_dev.copy_(hp_host, non_blocking=True)
+        agent.train_one_rollout()
+        epoch_metrics = agent.pop_epoch_metrics()                 # D2H: 40 doubles
+        roll_metrics = col.get_metrics()                          # D2H: running stats + episode window
+        weights_host.copy_(agent.policy_model.flat_params, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = steps_per_iter_local * world * e2e_steps / float(e2e_s.item())
+
+    # ---- roofline of the dominant kernel (the fused update kernel), timed alone on its own stream ----------------------
+    roof = kernel_rooflines(agent, cfg, dev) if rank == 0 else None
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(args, threads=1, budget_s=20.0)
+
+    if rank == 0:
+        peaks = _peaks()
+        line = {
+            "metric": "PPO env-steps/sec (collect+GAE+update)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/update), f64 (env physics)", "data": "synthetic",
+            "config": {"workload": "CartPole-v1:ppo, 65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP (BASELINE.json configs[1])",
+                       "n_envs_per_gpu": args.n_envs, "n_envs_total": args.n_envs * world, "n_steps": args.n_steps, "n_epochs": args.n_epochs,
+                       "batch_size_total": args.batch_size * world, "minibatches_per_step": launches_per_step(cfg, world) // 6,
+                       "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded, NCCL grad all-reduce per minibatch",
+                       "l2": "rollout working set (>=300 MB per GPU) exceeds the 126 MB L2; no explicit flush",
+                       "last_policy_loss": epoch_metrics.get("opt/loss/policy"), "last_ep_rew_mean": roll_metrics.get("roll/ep_rew/mean")},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "api": "PPOAgent.train_one_rollout() + pop_epoch_metrics() + RolloutCollector.get_metrics()"},
+            "gpu_launches": launches_per_step(cfg, world) * args.steps,
+            "roofline": roof["update"] if roof else None,
+            "roofline_gae": roof["gae"] if roof else None,
+            "roofline_collect": roof["collect"] if roof else None,
+            "cpu_baseline": cpu_base,
+            "peaks_source": peaks["source"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(agent, cfg, dev):
+    """Per-kernel achieved rates, each kernel timed alone with CUDA events on the launching stream."""
+    import ctypes as C
+    from gymnasium_solver_b200 import _native as N
+
+    peaks = _peaks()
+    col = agent.get_rollout_collector("train")
+    traj = col.collect()
+    torch.cuda.synchronize()
+    out = {}
+    reps = 20
+
+    def timed(fn, reps=reps):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    # fused update kernel (+ its two tiny reduction kernels): one minibatch per call, a different minibatch every call
+    batches = [b for _, _, b in agent.minibatches(traj, 12345)]
+    it = [0]
+
+    def one_update():
+        agent.losses_for_batch(batches[it[0] % len(batches)], 0)
+        it[0] += 1
+
+    t = timed(one_update)
+    hd = tuple(cfg.hidden_dims)
+    flops = FLOP_PER_SAMPLE_PASS.get(hd, 27264) * agent.local_batch_size
+    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    out["update"] = {"kernel": "update_kernel<64,64,128,PPO> (gs_ppo_step)", "bound": "fp32_simt", "achieved": flops / t / 1e12,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / fp32_peak, "traffic": None,
+                     "note": "fp32 FMA-pipe kernel (no tensor cores yet): peak = 148 SM x 128 FMA x 2 x sm_max_mhz; "
+                             f"vs measured bf16 tensor peak {peaks['bf16_tflops']:.0f} TF/s this is {flops / t / 1e12 / peaks['bf16_tflops']:.4f}",
+                     "algorithmic_flop_per_launch": flops, "avg_launch_s": t}
+    # GAE kernel
+    b = col._buffer
+    T, n = int(cfg.n_steps), agent.local_n_envs
+    adv, ret = torch.empty_like(b.rewards_buf), torch.empty_like(b.rewards_buf)
+
+    def one_gae():
+        N.check(N.lib().gs_gae(N.ptr(b.values_buf), N.ptr(b.rewards_buf), N.ptr(b.dones_buf), N.ptr(b.timeouts_buf), N.ptr(col._last_values),
+                               N.ptr(b.bootstrapped_values_buf), T, n, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.stream()))
+
+    t = timed(one_gae)
+    gbytes = GAE_BYTES_PER_ELEM * T * n
+    out["gae"] = {"kernel": "gae_kernel<HAS_BOOT>", "bound": "hbm", "achieved": gbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": gbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": gbytes, "avg_launch_s": t}
+
+    # fused collect kernel: 34 B/sample store traffic is the algorithmic HBM figure; it is compute (fp32 MLP + fp64 physics) bound
+    def one_collect():
+        col.collect()
+
+    t = timed(one_collect, reps=5)
+    cbytes = (34 + 12) * T * n
+    out["collect"] = {"kernel": "collect_kernel<64,64,64,CartPole> + GAE + stats", "bound": "hbm", "achieved": cbytes / t / 1e9,
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                      "env_steps_per_s": T * n / t, "avg_call_s": t,
+                      "note": "whole RolloutCollector.collect() call (collect kernel + GAE + moments); compute-bound, reported for reference"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------- CPU baseline
+def cpu_iteration(env, params, opt, n_envs, T, n_epochs, batch, obs, gen, hp):
+    """One reference-shaped training iteration on the CPU: per-step policy_act + env.step, numpy GAE, torch PPO update."""
+    from oracle import policy as P
+    from oracle import returns as R
+
+    D = obs.shape[1]
+    obs_buf = np.zeros((T, n_envs, D), np.float32)
+    act_buf = np.zeros((T, n_envs), np.int64)
+    logp_buf = np.zeros((T, n_envs), np.float32)
+    val_buf = np.zeros((T, n_envs), np.float32)
+    rew_buf = np.zeros((T, n_envs), np.float32)
+    done_buf = np.zeros((T, n_envs), bool)
+    to_buf = np.zeros((T, n_envs), bool)
+    with torch.no_grad():
+        for t in range(T):
+            u = torch.rand(n_envs, generator=gen)
+            a, lp, v, _ = P.act(params, torch.from_numpy(obs), uniforms=u)
+            obs_buf[t], act_buf[t], logp_buf[t], val_buf[t] = obs, a.numpy(), lp.numpy(), v.numpy()
+            obs, r, term, trunc, _ = env.step(a.numpy().astype(np.int32))
+            rew_buf[t], done_buf[t], to_buf[t] = r, term | trunc, trunc
+        _, last_v = P.forward(params, torch.from_numpy(obs))
+    adv, ret = R.gae(val_buf, rew_buf, done_buf, to_buf, last_v.numpy(), np.zeros_like(val_buf), 0.99, 0.95)
+    flat = lambda x: torch.from_numpy(np.ascontiguousarray(x.swapaxes(0, 1).reshape(n_envs * T, *x.shape[2:])))
+    data = [flat(obs_buf), flat(act_buf), flat(logp_buf), flat(val_buf), flat(adv), flat(ret)]
+    total = n_envs * T
+    for _ in range(n_epochs):
+        order = torch.argsort(torch.rand(total, generator=gen))
+        for k in range(total // batch):
+            idx = order[k * batch:(k + 1) * batch]
+            opt.zero_grad()
+            loss, _ = P.ppo_loss(params, *(d[idx] for d in data), **hp)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), 0.5)
+            opt.step()
+    return obs
+
+
+def cpu_baseline(args, threads: int, budget_s: float, steps: int | None = None, warmup: int = 0):
+    """The oracle port of the reference's CPU path on a bounded sample of the workload (same T, n_epochs, model;
+    fewer envs; minibatch count per pass preserved)."""
+    from oracle import envs as OE
+    from oracle import policy as P
+
+    torch.set_num_threads(max(1, threads))
+    n_envs = args.cpu_envs
+    T, n_epochs = args.n_steps, args.n_epochs
+    n_mb = max(1, (args.n_envs * args.n_steps) // args.batch_size)
+    batch = n_envs * T // n_mb
+    env = OE.OracleVecEnv("CartPole-v1", n_envs, seed=42, threads=threads)
+    obs, _ = env.reset()
+    hd = {"mlp_64x64": (64, 64), "mlp_medium": (256, 256), "mlp_small": (128, 128), "mlp_tiny": (64,)}[args.model_id]
+    params = {k: v.requires_grad_(True) for k, v in P.init_params(4, hd, 2, seed=0).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=3e-4)
+    gen = torch.Generator().manual_seed(0)
+    hp = dict(clip_range=0.2, clip_range_vf=0.2, vf_coef=0.5, ent_coef=0.0, normalize_adv=True)
+    for _ in range(warmup):
+        obs = cpu_iteration(env, params, opt, n_envs, T, n_epochs, batch, obs, gen, hp)
+    t0, done_iters = time.perf_counter(), 0
+    while True:
+        obs = cpu_iteration(env, params, opt, n_envs, T, n_epochs, batch, obs, gen, hp)
+        done_iters += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done_iters >= steps) or (steps is None and el >= budget_s):
+            break
+    return {"value": n_envs * T * done_iters / el, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{done_iters} iteration(s) of {n_envs} envs x {T} steps, {n_epochs} passes x {n_mb} minibatches of {batch}, "
+                      f"oracle C env loop + torch CPU policy/loss + numpy GAE, {el:.1f} s",
+            "host_cores_available": os.cpu_count(), "torch_threads": torch.get_num_threads(), "seconds": el}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on all host threads; rank 0 only."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    threads = os.cpu_count() or 1
+    args.cpu_envs = max(args.cpu_envs, 2048)
+    base = cpu_baseline(args, threads=threads, budget_s=0.0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    per_step_ms = base["seconds"] / max(1, args.steps) * 1e3
+    line = {"impl": "reference", "metric": "PPO env-steps/sec (collect+GAE+update)", "value": base["value"], "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/update), f64 (env physics)", "data": "synthetic",
+            "config": {"workload": "CartPole-v1:ppo, n_steps=128, 64x64 MLP, 10 passes x 8 minibatches (BASELINE.json configs[1]); "
+                                   f"bounded sample of {args.cpu_envs} envs per step on the host CPU", "model_id": args.model_id,
+                       "n_steps": args.n_steps, "n_epochs": args.n_epochs},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--n-steps", type=int, default=128)
+    ap.add_argument("--batch-size", type=int, default=1048576, help="minibatch per GPU")
+    ap.add_argument("--n-epochs", type=int, default=10)
+    ap.add_argument("--model-id", default="mlp_64x64")
+    ap.add_argument("--track-activations", type=int, default=1)
+    ap.add_argument("--cpu-envs", type=int, default=512, help="envs of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,13 +82,14 @@ SIGNATURES = {
     "gs_env_set_state": (_i32, [_vp, _vp, _vp, _vp]),
     "gs_env_get_state": (_i32, [_vp, _vp, _vp, _vp]),
     "gs_env_reset": (_i32, [_vp, _vp, _vp]),
-    "gs_env_step": (_i32, [_vp] * 10),
+    "gs_env_step": (_i32, [_vp] * 9),
     "gs_wrapper_attach": (_i32, [_vp, _i32, C.POINTER(_f64), _i32]),
     "gs_policy_act": (_i32, [C.POINTER(GsMlp), _vp, _i64, _u64, _u64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gs_policy_values": (_i32, [C.POINTER(GsMlp), _vp, _i64, _vp, _vp]),
     "gs_rollout_collect": (_i32, [_vp, C.POINTER(GsMlp), C.POINTER(GsRollout), _vp, _u64, _u64, _i32, _vp]),
     "gs_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _f64, _vp, _vp, _vp]),
     "gs_mc_returns": (_i32, [_vp, _vp, _vp, _i32, _i64, _f64, _i32, _vp, _vp, _vp]),
+    "gs_returns_to_full_episode": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "gs_valid_index_map": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gs_valid_index_map_workspace_bytes": (_i64, [_i64]),
     "gs_moments": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),

@@ -1,0 +1,426 @@
+"""BaseAgent on the CUDA engine (reference: agents/base_agent.py).
+
+Keeps the reference's agent surface — ``build_env`` / ``build_models`` / ``build_rollout_collector`` / ``losses_for_batch`` /
+``training_step`` / ``_backpropagate_and_step`` / ``configure_optimizers`` / ``learn`` / ``save_checkpoint`` /
+``load_checkpoint`` and the hook order of one "epoch" = one rollout + ``n_epochs`` passes over it (reference
+agents/base_agent.py:253-366) — without PyTorch-Lightning: ``learn()`` drives the hooks itself.
+
+Engine mapping of one epoch:
+  collect                       1 fused collect launch + 1 target kernel                     (RolloutCollector.collect)
+  for pass, minibatch           gs_batch_moments -> gs_ppo_step / gs_reinforce_step (forward + loss + backward, gradients
+                                written into the flat .grad buffer) -> [NCCL all-reduce] -> gs_clip_grad_norm ->
+                                torch optimizer.step()
+Metrics stay on device as a running sum and reach the host once per epoch.
+Data parallel: one process per GPU owns ``n_envs / world_size`` envs (global env ids keep RNG streams W-invariant); the
+only data-path collective is the gradient all-reduce per minibatch (+ one tiny all-reduce of the per-minibatch
+advantage moments per pass so "batch" normalisation means the GLOBAL minibatch).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+import time
+from pathlib import Path
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ..utils.environment import build_env_from_config
+from ..utils.optimizer_factory import build_optimizer
+from ..utils.policy_factory import build_policy_from_env_and_config
+from ..utils.rollout_collector import DeviceTrajectory, RolloutCollector
+from ..utils.rollout_buffer import RolloutTrajectory
+
+STAGES = ["train", "val", "test"]
+_SPLITMIX = 0x9E3779B97F4A7C15
+
+
+def _mix64(x: int) -> int:
+    x = (x + _SPLITMIX) & (2**64 - 1)
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+    return x ^ (x >> 31)
+
+
+class EngineBatch:
+    """One minibatch for the update kernels: a gs_batch_t over the rollout's time-major arrays plus what keeps it alive."""
+
+    def __init__(self, struct: N.GsBatch, keep, n: int):
+        self.struct, self.keep, self.n = struct, keep, int(n)
+
+    def __len__(self):
+        return self.n
+
+
+class EngineLoss:
+    """What ``losses_for_batch`` returns as "loss": the gradients already sit in ``policy_model.flat_grads`` (forward,
+    loss and backward are one kernel), so ``backward()`` is a no-op; ``item()`` reads the scalar (one D2H copy)."""
+
+    def __init__(self, metrics: torch.Tensor):
+        self.metrics = metrics
+
+    def backward(self):
+        return None
+
+    def detach(self):
+        return self.metrics[N.M["opt/loss/total"]]
+
+    def item(self) -> float:
+        return float(self.metrics[N.M["opt/loss/total"]].item())
+
+    __float__ = item
+
+
+class MetricsRecorder:
+    """Per-epoch metric aggregation (reference: utils/metrics_recorder.py + metrics_buffer.py): host scalars are averaged
+    per epoch; the engine's per-minibatch metric vectors are summed ON DEVICE and folded in at epoch end."""
+
+    def __init__(self):
+        self._host: Dict[str, Dict[str, list]] = {}
+        self.history: list[Dict[str, Any]] = []
+
+    def record(self, stage: str, metrics: Dict[str, Any]) -> None:
+        bucket = self._host.setdefault(stage, {})
+        for k, v in metrics.items():
+            if v is None:
+                continue
+            v = float(v.item()) if isinstance(v, torch.Tensor) else float(v)
+            assert math.isfinite(v), f"metric {k} is not finite: {v}"
+            bucket.setdefault(k, []).append(v)
+
+    def epoch_means(self, stage: str, reset: bool = True) -> Dict[str, float]:
+        bucket = self._host.get(stage, {})
+        out = {k: sum(v) / len(v) for k, v in bucket.items() if v}
+        if reset:
+            self._host[stage] = {}
+        return out
+
+
+class BaseAgent(nn.Module):
+    def __init__(self, config, *, device=None, rank: Optional[int] = None, world_size: Optional[int] = None):
+        super().__init__()
+        self.config = config
+        self.rank = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
+        self.world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else int(world_size)
+        if not torch.cuda.is_available():
+            raise N.EngineError("the b200 engine needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.policy_model = None
+        self._envs: Dict[str, Any] = {}
+        self._rollout_collectors: Dict[str, RolloutCollector] = {}
+        self._trajectories = None
+        self._early_stop_epoch = False
+        self._early_stop_reason = ""
+        self._optimizer = None
+        self.current_epoch = 0
+        self.should_stop = False
+        self.best_eval_reward = -float("inf")
+
+        # schedulable hyperparameters (reference agents/base_agent.py:72-77)
+        self.policy_lr = config.policy_lr
+        self.clip_range = getattr(config, "clip_range", None)
+        self.vf_coef = getattr(config, "vf_coef", None)
+        self.ent_coef = config.ent_coef
+        self.n_epochs = config.n_epochs
+        self.metrics_recorder = MetricsRecorder()
+
+        if int(config.n_envs) % self.world_size != 0:
+            raise ValueError(f"n_envs={config.n_envs} must be divisible by world_size={self.world_size}")
+        if int(config.batch_size) % self.world_size != 0:
+            raise ValueError(f"batch_size={config.batch_size} must be divisible by world_size={self.world_size}")
+        self.local_n_envs = int(config.n_envs) // self.world_size
+        self.local_batch_size = int(config.batch_size) // self.world_size
+
+        for stage in STAGES:
+            self.build_env(stage)
+        self.build_models()
+        for stage in STAGES:
+            self.build_rollout_collector(stage)
+
+        # device scratch of the update path
+        mlp = N.mlp_struct(self.policy_model)
+        self._ws_bytes = N.lib().gs_update_workspace_bytes(C.byref(mlp), self.device.index)
+        if self._ws_bytes <= 0:
+            raise N.EngineError(N.lib().gs_last_error().decode())
+        self._workspace = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+        self._metrics_dev = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
+        self._metrics_sum = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
+        self._metrics_n = 0
+        self._moments = None
+
+    # ------------------------------------------------------------------------------------------------ construction
+    def build_env(self, stage: str, **kwargs):
+        cfg = self.config
+        seed = {"train": cfg.seed_train, "val": cfg.seed_val, "test": cfg.seed_test}[stage]
+        with torch.cuda.device(self.device):
+            env = build_env_from_config(cfg, seed=seed, n_envs=self.local_n_envs, device=self.device,
+                                        env_id_offset=self.rank * self.local_n_envs, **kwargs)
+        self._envs[stage] = env
+        return env
+
+    def get_env(self, stage: str):
+        return self._envs[stage]
+
+    def build_models(self):
+        """reference agents/base_agent.py:103-106 — then move to the GPU and flatten parameter / grad storage."""
+        torch.manual_seed(int(self.config.seed))        # identical initial weights on every rank
+        model = build_policy_from_env_and_config(self.get_env("train"), self.config)
+        model.to(self.device)
+        model.flatten_parameters_()
+        self.policy_model = model
+
+    def build_rollout_collector(self, stage: str):
+        kw = self.config.get_rollout_collector_kwargs()
+        # val / test collectors read the SAME parameter storage: evaluation sees the current weights without copies
+        col = RolloutCollector(self.get_env(stage), self.policy_model, store_next_obs=bool(self.config.store_next_obs),
+                               rng_seed=_mix64(int(self.config.seed) * 3 + STAGES.index(stage)) >> 1, **kw)
+        self._rollout_collectors[stage] = col
+        return col
+
+    def get_rollout_collector(self, stage: str) -> RolloutCollector:
+        return self._rollout_collectors[stage]
+
+    # ------------------------------------------------------------------------------------------------ to override
+    def losses_for_batch(self, batch, batch_idx):
+        raise NotImplementedError("Subclasses must implement losses_for_batch")
+
+    # ------------------------------------------------------------------------------------------------ optimisation
+    def configure_optimizers(self):
+        return build_optimizer(params=self.policy_model.parameters(), optimizer=self.config.optimizer, lr=self.policy_lr)
+
+    def optimizers(self):
+        if self._optimizer is None:
+            self._optimizer = self.configure_optimizers()
+        return self._optimizer
+
+    def _change_optimizers_lr(self, lr: float) -> None:
+        for group in self.optimizers().param_groups:
+            group["lr"] = lr
+
+    def set_hyperparameter(self, name: str, value: float) -> None:
+        setattr(self, name, value)
+        if name == "policy_lr":
+            self._change_optimizers_lr(value)
+
+    def _as_engine_batch(self, batch) -> EngineBatch:
+        """Accept the engine's own minibatch descriptor or a reference-style gathered RolloutTrajectory (flat tensors)."""
+        if isinstance(batch, EngineBatch):
+            return batch
+        f = lambda x, dt: x.detach().to(device=self.device, dtype=dt).contiguous()
+        obs = f(batch.observations, torch.float32)
+        B = obs.shape[0]
+        arrs = dict(obs=obs.reshape(1, B, -1), actions=f(batch.actions, torch.int32).reshape(1, B),
+                    logprobs=f(batch.logprobs, torch.float32).reshape(1, B), values=f(batch.values, torch.float32).reshape(1, B),
+                    adv=f(batch.advantages, torch.float32).reshape(1, B), ret=f(batch.returns, torch.float32).reshape(1, B))
+        return self._make_batch(arrs, 1, B, n=B)
+
+    def _make_batch(self, tm: dict, T: int, n_envs: int, *, n: int, idx=None, perm_key: int = 0, perm_offset: int = 0,
+                    perm_len: int = 0, idx_map=None) -> EngineBatch:
+        b = N.GsBatch()
+        b.T, b.N, b.obs_dim = T, n_envs, tm["obs"].shape[-1]
+        b.obs, b.actions, b.logp_old = N.ptr(tm["obs"]), N.ptr(tm["actions"]), N.ptr(tm["logprobs"])
+        b.values_old, b.adv, b.ret = N.ptr(tm["values"]), N.ptr(tm["adv"]), N.ptr(tm["ret"])
+        b.n, b.idx, b.perm_key, b.perm_offset, b.perm_len = n, N.ptr(idx), perm_key, perm_offset, perm_len
+        b.idx_map = N.ptr(idx_map)
+        return EngineBatch(b, (tm, idx, idx_map), n)
+
+    def training_step(self, batch, batch_idx):
+        """reference agents/base_agent.py:330-366."""
+        if self._early_stop_epoch:
+            return None
+        result = self.losses_for_batch(batch, batch_idx)
+        if result["early_stop_epoch"]:
+            self._early_stop_epoch = True
+            return None
+        self._backpropagate_and_step(result["loss"])
+        return None
+
+    def _backpropagate_and_step(self, losses):
+        """reference agents/base_agent.py:591-621: grads -> group norms (pre-clip) -> global-norm clip -> optimizer step.
+        The gradients were produced by the fused kernel; with several ranks they are averaged over NVLink first."""
+        opt = self.optimizers()
+        model = self.policy_model
+        if self.world_size > 1:
+            torch.distributed.all_reduce(model.flat_grads, op=torch.distributed.ReduceOp.AVG)
+        mlp = N.mlp_struct(model)
+        max_norm = float(self.config.max_grad_norm) if self.config.max_grad_norm is not None else 0.0
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_clip_grad_norm(C.byref(mlp), N.ptr(model.flat_grads), max_norm, N.ptr(self._metrics_dev), N.stream()))
+        self._metrics_sum += self._metrics_dev
+        self._metrics_n += 1
+        opt.step()
+
+    # ------------------------------------------------------------------------------------------------ one epoch
+    def minibatches(self, traj: DeviceTrajectory, epoch_key: int):
+        """n_epochs passes of rollout/batch minibatches (reference: MultiPassRandomSampler, utils/samplers.py:29-34).
+        "device" shuffle: pass p is the keyed bijection pi_{key(epoch,p)} evaluated inside the kernel; "torch" shuffle:
+        argsort(rand) index tensors like the reference."""
+        total = len(traj)
+        B = self.local_batch_size
+        if total % B != 0:
+            raise ValueError(f"Batch size must divide rollout size exactly: data_len={total}, batch_size={B}.")
+        n_mb = total // B
+        tm, idx_map = traj.tm, traj.tm.get("idx_map")
+        for p in range(int(self.n_epochs)):
+            if self.config.minibatch_shuffle == "torch":
+                g = getattr(self, "_shuffle_gen", None)
+                if g is None:
+                    g = self._shuffle_gen = torch.Generator(device=self.device).manual_seed(int(self.config.seed))
+                order = torch.argsort(torch.rand(total, generator=g, device=self.device))
+                for k in range(n_mb):
+                    idx = order[k * B:(k + 1) * B].contiguous()
+                    yield p, k, self._make_batch(tm, traj.T, traj.n_envs, n=B, idx=idx, idx_map=idx_map)
+            else:
+                key = _mix64(epoch_key * 1315423911 + p)
+                for k in range(n_mb):
+                    yield p, k, self._make_batch(tm, traj.T, traj.n_envs, n=B, perm_key=key, perm_offset=k * B, perm_len=total, idx_map=idx_map)
+
+    def train_on_rollout(self, traj: DeviceTrajectory) -> None:
+        self._early_stop_epoch = False
+        key = _mix64(int(self.config.seed) ^ (self.current_epoch * 0x100000001B3))
+        for _, k, batch in self.minibatches(traj, key):
+            self.training_step(batch, k)
+
+    def train_one_rollout(self) -> DeviceTrajectory:
+        """collect + targets + all minibatch passes: the unit the headline metric counts env-steps over."""
+        traj = self.get_rollout_collector("train").collect()
+        self._trajectories = traj
+        self.train_on_rollout(traj)
+        return traj
+
+    def pop_epoch_metrics(self) -> Dict[str, float]:
+        """Epoch means of the engine's per-minibatch metrics (one D2H copy)."""
+        out = {}
+        if self._metrics_n > 0:
+            mean = (self._metrics_sum / self._metrics_n).cpu().numpy()
+            out = {k: float(mean[i]) for i, k in enumerate(N.METRIC_KEYS)}
+            self._metrics_sum.zero_()
+            self._metrics_n = 0
+        out.update(self.metrics_recorder.epoch_means("train"))
+        return out
+
+    # ------------------------------------------------------------------------------------------------ schedules
+    def calc_training_progress(self) -> float:
+        if self.config.max_env_steps is None:
+            return 0.0
+        total = self.get_rollout_collector("train").total_steps * self.world_size
+        return max(0.0, min(total / float(self.config.max_env_steps), 1.0))
+
+    def _apply_schedules(self) -> None:
+        """reference trainer_callbacks/hyperparameter_scheduler.py:76-113 (linear / cosine / exponential)."""
+        cfg = self.config
+        steps = self.get_rollout_collector("train").total_steps * self.world_size
+        for param in ("policy_lr", "ent_coef", "vf_coef", "clip_range", "clip_range_vf"):
+            kind = getattr(cfg, f"{param}_schedule", None)
+            if not kind:
+                continue
+            v0, v1 = getattr(cfg, f"{param}_schedule_start_value"), getattr(cfg, f"{param}_schedule_end_value")
+            p0, p1 = getattr(cfg, f"{param}_schedule_start"), getattr(cfg, f"{param}_schedule_end")
+            to_steps = lambda p: p * cfg.max_env_steps if p <= 1.0 else p
+            s0, s1 = to_steps(p0), to_steps(p1)
+            frac = min(1.0, max(0.0, (steps - s0) / max(s1 - s0, 1e-12)))
+            if kind == "cosine":
+                val = v1 + (v0 - v1) * 0.5 * (1.0 + math.cos(math.pi * frac))
+            elif kind == "exponential":
+                val = v0 * (v1 / v0) ** frac if v0 > 0 and v1 > 0 else v0 + (v1 - v0) * frac
+            else:
+                val = v0 + (v1 - v0) * frac
+            self.set_hyperparameter(param, val)
+
+    # ------------------------------------------------------------------------------------------------ fit loop
+    def learn(self, *, log_fn=None, max_epochs: Optional[int] = None) -> Dict[str, Any]:
+        """Built-in fit loop with the reference's hook order."""
+        cfg = self.config
+        col = self.get_rollout_collector("train")
+        t0 = time.time()
+        history = []
+        max_epochs = max_epochs if max_epochs is not None else cfg.max_epochs
+        reason = ""
+        while True:
+            # on_train_epoch_start: budget check before collecting (reference agents/base_agent.py:306-320)
+            if cfg.max_env_steps is not None:
+                cur = col.total_steps * self.world_size
+                nxt = int(cfg.n_envs) * int(cfg.n_steps)
+                if cur + nxt > cfg.max_env_steps:
+                    reason = f"'train/cnt/total_env_steps': {cur} + {nxt} would exceed {int(cfg.max_env_steps)}."
+                    break
+            if max_epochs is not None and self.current_epoch >= max_epochs:
+                reason = f"max_epochs={max_epochs} reached."
+                break
+            self.train_one_rollout()
+            # on_train_epoch_end: metrics, schedules, early stopping
+            row = {"epoch": self.current_epoch, "time_s": time.time() - t0}
+            row.update({f"train/{k}": v for k, v in col.get_metrics().items() if k != "action_dist"})
+            row.update({f"train/{k}": v for k, v in self.pop_epoch_metrics().items()})
+            row["train/cnt/total_env_steps"] = col.total_steps * self.world_size
+            self._apply_schedules()
+            thr = cfg.early_stop_on_train_threshold
+            if thr and "train/roll/ep_rew/mean" in row:
+                limit = self.get_env("train").get_return_threshold() if thr is True else float(thr)
+                if row["train/roll/ep_rew/mean"] >= limit:
+                    reason = f"train/roll/ep_rew/mean {row['train/roll/ep_rew/mean']:.2f} >= {limit}"
+                    self.should_stop = True
+            if cfg.eval_freq_epochs and (self.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
+                    and self.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
+                ev = self.evaluate("val")
+                row.update({f"val/{k}": v for k, v in ev.items()})
+                mean = ev.get("roll/ep_rew/mean")
+                if mean is not None:
+                    self.best_eval_reward = max(self.best_eval_reward, mean)
+                    thr = cfg.early_stop_on_eval_threshold
+                    if thr:
+                        limit = cfg.reward_threshold if cfg.reward_threshold is not None else self.get_env("val").get_return_threshold()
+                        limit = limit if thr is True else float(thr)
+                        if mean >= limit:
+                            reason = f"val/roll/ep_rew/mean {mean:.2f} >= {limit}"
+                            self.should_stop = True
+            history.append(row)
+            if log_fn is not None and self.rank == 0:
+                log_fn(row)
+            self.current_epoch += 1
+            if self.should_stop:
+                break
+        self._early_stop_reason = reason
+        return {"history": history, "stop_reason": reason, "epochs": self.current_epoch, "elapsed_s": time.time() - t0,
+                "total_env_steps": col.total_steps * self.world_size, "best_eval_reward": self.best_eval_reward}
+
+    def evaluate(self, stage: str = "val") -> Dict[str, Any]:
+        col = self.get_rollout_collector(stage)
+        per_rank = max(1, int(self.config.eval_episodes) // self.world_size)
+        return col.evaluate_episodes(n_episodes=per_rank, deterministic=bool(self.config.eval_deterministic))
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, checkpoint_dir) -> None:
+        """model.pt / optimizer.pt / state.json like the reference (agents/base_agent.py:658-732), plus the device env
+        state and RNG counters the reference cannot resume (TODO.md:29)."""
+        d = Path(checkpoint_dir)
+        d.mkdir(parents=True, exist_ok=True)
+        torch.save(self.policy_model.state_dict(), d / "model.pt")
+        torch.save(self.optimizers().state_dict(), d / "optimizer.pt")
+        col = self.get_rollout_collector("train")
+        env_state, elapsed = self.get_env("train").get_state()
+        torch.save({"state": env_state.cpu(), "elapsed": elapsed.cpu(), "obs": None if col.obs is None else col.obs.cpu()}, d / "env_state.pt")
+        state = {"epoch": self.current_epoch, "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
+                 "best_episode_reward": col._best_episode_reward if math.isfinite(col._best_episode_reward) else None,
+                 "best_eval_reward": self.best_eval_reward if math.isfinite(self.best_eval_reward) else None,
+                 "algo_id": self.config.algo_id, "env_id": self.config.env_id, "rng_seed": col.rng_seed}
+        (d / "state.json").write_text(json.dumps(state, indent=2))
+
+    def load_checkpoint(self, checkpoint_dir, *, resume_training: bool = True) -> None:
+        d = Path(checkpoint_dir)
+        self.policy_model.load_state_dict(torch.load(d / "model.pt", map_location=self.device))
+        if not resume_training:
+            return
+        self.optimizers().load_state_dict(torch.load(d / "optimizer.pt", map_location=self.device))
+        state = json.loads((d / "state.json").read_text())
+        col = self.get_rollout_collector("train")
+        self.current_epoch = int(state["epoch"])
+        col.total_steps, col.total_vec_steps = int(state["total_env_steps"]), int(state["total_vec_steps"])
+        if state.get("best_episode_reward") is not None:
+            col._best_episode_reward = float(state["best_episode_reward"])
+        if state.get("best_eval_reward") is not None:
+            self.best_eval_reward = float(state["best_eval_reward"])

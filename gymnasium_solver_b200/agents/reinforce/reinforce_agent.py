@@ -1,0 +1,47 @@
+"""REINFORCEAgent on the CUDA engine (reference: agents/reinforce/reinforce_agent.py:8-88).
+
+loss = -(logp * target).mean() + ent_coef * (-entropy.mean()), target = returns or advantages (optionally batch
+normalised), fused with the MLP forward / backward like PPO.  The reference reads ``config.normalize_advantages`` which
+its REINFORCEConfig never declares; here the field exists and defaults to "off"."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ... import _native as N
+from ..base_agent import BaseAgent, EngineLoss
+
+
+class REINFORCEAgent(BaseAgent):
+    def __init__(self, config, **kw):
+        super().__init__(config, **kw)
+        self._mom = torch.zeros(2, 3, dtype=torch.float64, device=self.device)
+
+    def losses_for_batch(self, batch, batch_idx):
+        cfg = self.config
+        if cfg.policy_targets not in ("returns", "advantages"):
+            raise ValueError(f"Invalid policy targets: {cfg.policy_targets}")
+        b = self._as_engine_batch(batch)
+        model = self.policy_model
+        mlp = N.mlp_struct(model)
+        hp = N.GsReinforceHparams()
+        hp.ent_coef = float(self.ent_coef)
+        hp.policy_targets = 0 if cfg.policy_targets == "returns" else 1
+        hp.normalize_returns = int(cfg.normalize_returns == "batch")
+        hp.normalize_adv = int(getattr(cfg, "normalize_advantages", "off") == "batch")
+        hp.track_activations = int(bool(getattr(cfg, "track_activations", True)))
+        L = N.lib()
+        with torch.cuda.device(self.device):
+            st = N.stream()
+            if hp.normalize_returns or hp.normalize_adv:
+                self._mom.zero_()
+                if hp.normalize_returns:
+                    N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.ret, N.ptr(self._mom[0]), st))
+                if hp.normalize_adv:
+                    N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._mom[1]), st))
+                if self.world_size > 1:
+                    torch.distributed.all_reduce(self._mom)
+            N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(self._mom[0]), N.ptr(self._mom[1]),
+                                        N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
+        return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=False)

@@ -114,6 +114,22 @@ mc_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, 
     }
 }
 
+// convert_returns_to_full_episode as a standalone in-place pass (the fused path is mc_kernel's episode_mode)
+template <bool HAS_TO>
+__global__ void __launch_bounds__(kScanThreads)
+full_episode_kernel(float* __restrict__ ret, const uint8_t* __restrict__ dones, const uint8_t* __restrict__ timeouts, int T, int64_t N) {
+    const int64_t n = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
+    if (n >= N) return;
+    float seg = 0.0f;
+    bool start = true;
+    for (int t = 0; t < T; ++t) {
+        const int64_t o = (int64_t)t * N + n;
+        if (start) seg = ret[o];
+        else ret[o] = seg;
+        start = __ldg(dones + o) && !(HAS_TO && __ldg(timeouts + o));
+    }
+}
+
 // ---- valid mask / index map ------------------------------------------------------------------------------------------
 // inc[e] = largest env index e' <= e that has a real terminal (-1 if none): block-local inclusive max-scan + block maxima
 __global__ void valid_scan_local_kernel(const int32_t* __restrict__ last_terminal, int64_t N, int32_t* __restrict__ inc,
@@ -245,6 +261,17 @@ int gs_mc_returns(const float* rewards, const uint8_t* dones, const uint8_t* tim
     cudaStream_t st = (cudaStream_t)stream;
     if (timeouts) mc_kernel<true><<<blocks, kScanThreads, 0, st>>>(rewards, dones, timeouts, T, N, (float)gamma, episode_mode, ret, last_terminal);
     else mc_kernel<false><<<blocks, kScanThreads, 0, st>>>(rewards, dones, nullptr, T, N, (float)gamma, episode_mode, ret, last_terminal);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_returns_to_full_episode(float* ret, const uint8_t* dones, const uint8_t* timeouts, int T, int64_t N, void* stream) {
+    if (!ret || !dones) GS_FAIL("gs_returns_to_full_episode: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_returns_to_full_episode: empty rollout");
+    const unsigned blocks = (unsigned)((N + kScanThreads - 1) / kScanThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (timeouts) full_episode_kernel<true><<<blocks, kScanThreads, 0, st>>>(ret, dones, timeouts, T, N);
+    else full_episode_kernel<false><<<blocks, kScanThreads, 0, st>>>(ret, dones, nullptr, T, N);
     GS_LAUNCH_CHECK();
     return 0;
 }

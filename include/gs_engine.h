@@ -219,6 +219,9 @@ int gs_gae(const float* values, const float* rewards, const uint8_t* dones, cons
  * the per-env fact behind _build_valid_mask_and_index_map :33-52. */
 int gs_mc_returns(const float* rewards, const uint8_t* dones, const uint8_t* timeouts, int T, int64_t N,
                   double gamma, int episode_mode, float* ret, int32_t* last_terminal, void* stream);
+/* convert_returns_to_full_episode :93-113 as a standalone in-place pass over reward-to-go returns (T,N) */
+int gs_returns_to_full_episode(float* ret, const uint8_t* dones, const uint8_t* timeouts /* nullable */, int T, int64_t N,
+                               void* stream);
 /* _build_valid_mask_and_index_map :33-52 + _build_idx_map_from_valid_mask :19-30, env-major (N*T,).
  * n_valid (device int64[1]) receives the number of valid entries (0 => reference returns None). */
 int gs_valid_index_map(const int32_t* last_terminal, int T, int64_t N, uint8_t* valid_mask, int64_t* idx_map,

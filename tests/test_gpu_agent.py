@@ -1,0 +1,203 @@
+"""GPU tests of the host-side mirror of the reference surface on top of the engine: RolloutCollector (fused collect,
+targets, lazy env-major trajectory, metrics, evaluate_episodes, MC path), PPOAgent / REINFORCEAgent (losses_for_batch on
+reference-style batches, full iterations) and learning on the reference's own CartPole-v1:ppo configuration."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import policy as OP
+from oracle import returns as OR
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(env="CartPole-v1", variant="ppo", **over):
+    from gymnasium_solver_b200.utils.config import load_config
+
+    cfg = load_config(env, variant)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    if "model_id" in over:
+        from gymnasium_solver_b200.utils.model_registry import resolve_model_spec
+        cfg._hidden_dims = resolve_model_spec(over["model_id"]).hidden_dims
+    cfg.validate()
+    return cfg
+
+
+def _oracle_params(model):
+    sd = model.state_dict()
+    return {k: sd[n].detach().cpu().clone() for k, n in zip(OP.PARAM_ORDER, sd.keys())}
+
+
+def test_collector_trajectory_layout_targets_and_metrics():
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.rollout_buffer import RolloutTrajectory
+
+    cfg = _cfg(n_envs=24, n_steps=40, batch_size=960, model_id="mlp_64x64", store_next_obs=True, max_episode_steps=25)
+    agent = build_agent(cfg, rank=0, world_size=1)
+    col = agent.get_rollout_collector("train")
+    traj = col.collect()
+    T, n = 40, 24
+    assert len(traj) == T * n and len(traj.observations) == T * n
+    assert traj._fields == RolloutTrajectory._fields
+    assert traj.observations.shape == (T * n, 4) and traj.actions.dtype == torch.int64 and traj.dones.dtype == torch.bool
+    tm = {k: v.cpu().numpy() for k, v in traj.tm.items() if isinstance(v, torch.Tensor)}
+    # env-major order: sample i = env * T + t  (reference tests/test_rollout_buffer.py:82-126)
+    for name, src in (("observations", "obs"), ("rewards", "rewards"), ("logprobs", "logprobs"), ("advantages", "adv"), ("returns", "ret"),
+                      ("next_observations", "next_obs")):
+        got = getattr(traj, name).cpu().numpy()
+        np.testing.assert_array_equal(got, tm[src].swapaxes(0, 1).reshape(T * n, *tm[src].shape[2:]), err_msg=name)
+    # next_obs[t] == obs[t+1] along the vector step axis
+    np.testing.assert_array_equal(tm["next_obs"][:-1], tm["obs"][1:])
+    # targets: GAE with the reference's zero bootstrapped array, bit-exact
+    adv, ret = OR.gae(tm["values"], tm["rewards"], tm["dones"], tm["timeouts"], col._last_values.cpu().numpy(), np.zeros_like(tm["values"]),
+                      cfg.gamma, cfg.gae_lambda)
+    np.testing.assert_array_equal(tm["adv"], adv)
+    np.testing.assert_array_equal(tm["ret"], ret)
+    # NEXT_STEP autoreset: the step after a done carries reward 0 and no flags
+    d = tm["dones"].astype(bool)
+    assert d.sum() > 0 and (tm["rewards"][1:][d[:-1]] == 0).all() and not d[1:][d[:-1]].any()
+    # policy outputs match the oracle forward of the same weights
+    p = _oracle_params(agent.policy_model)
+    logits, value = OP.forward(p, torch.from_numpy(tm["obs"].reshape(-1, 4)))
+    np.testing.assert_allclose(value.numpy(), tm["values"].reshape(-1), rtol=1e-5, atol=2e-6)
+    # metrics: reference key set and values recomputed from the buffers
+    m = col.get_metrics()
+    for k in ("cnt/total_env_steps", "cnt/total_vec_steps", "cnt/total_episodes", "cnt/total_rollouts", "roll/env_steps", "roll/vec_steps",
+              "roll/episodes", "roll/fps", "roll/obs/mean", "roll/obs/std", "roll/reward/mean", "roll/reward/std", "roll/return/mean",
+              "roll/return/std", "roll/adv/mean", "roll/adv/std", "roll/actions/mean", "roll/actions/std", "action_dist", "roll/baseline/mean",
+              "roll/baseline/std", "roll/ep_rew/mean", "roll/ep_len/mean", "roll/ep_rew/best", "roll/ep_rew/last", "roll/ep_len/last"):
+        assert k in m, k
+    assert m["cnt/total_env_steps"] == T * n and m["cnt/total_vec_steps"] == T and m["roll/episodes"] == int(d.sum())
+    np.testing.assert_allclose(m["roll/obs/mean"], tm["obs"].mean(dtype=np.float64), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(m["roll/reward/mean"], tm["rewards"].mean(dtype=np.float64), rtol=1e-6)
+    np.testing.assert_allclose(m["roll/adv/std"], tm["adv"].astype(np.float64).std(), rtol=1e-5)
+    np.testing.assert_array_equal(m["action_dist"], np.bincount(tm["actions"].ravel(), minlength=2))
+    ep_r = agent.get_rollout_collector("train")._buffer.ep_return_buf.cpu().numpy()[d]  # (step, env) order == row-major
+    np.testing.assert_allclose(m["roll/ep_rew/mean"], ep_r[-100:].mean(), rtol=1e-9)
+    assert m["roll/ep_rew/best"] == ep_r.max() and m["roll/ep_rew/last"] == ep_r[-1]
+    # slice_trajectories == fancy indexing of the env-major tensors (reference rollout_collector.py:657-682)
+    idx = [5, 0, 17, 959]
+    sl = col.slice_trajectories(traj, idx)
+    np.testing.assert_array_equal(sl.observations.cpu().numpy(), traj.observations.cpu().numpy()[idx])
+    np.testing.assert_array_equal(sl.advantages.cpu().numpy(), traj.advantages.cpu().numpy()[idx])
+
+
+def test_collector_mc_path_baseline_index_map_and_episode_mode():
+    from gymnasium_solver_b200.agents import build_agent
+
+    for variant_rt in ("mc:rtg", "mc:episode"):
+        cfg = _cfg("CartPole-v1", "reinforce", n_envs=16, n_steps=64, batch_size=1024, returns_type=variant_rt, max_episode_steps=30)
+        agent = build_agent(cfg, rank=0, world_size=1)
+        col = agent.get_rollout_collector("train")
+        base = OR.RunningStats()
+        for it in range(2):
+            traj = col.collect()
+            tm = {k: v.cpu().numpy() for k, v in traj.tm.items() if isinstance(v, torch.Tensor)}
+            zeros = np.zeros_like(tm["timeouts"])
+            exp_ret = OR.mc_returns(tm["rewards"], tm["dones"], zeros, cfg.gamma)
+            if variant_rt == "mc:episode":
+                exp_ret = OR.to_full_episode(exp_ret, tm["dones"], zeros)
+            np.testing.assert_array_equal(tm["ret"], exp_ret)
+            vm, im = OR.valid_mask_and_index_map(tm["dones"], zeros)
+            np.testing.assert_array_equal(tm["idx_map"], im)
+            base.update(exp_ret.swapaxes(0, 1).reshape(-1)[vm])
+            np.testing.assert_allclose(tm["adv"], exp_ret - np.float32(base.mean()), rtol=1e-5, atol=1e-5)
+        m = col.get_metrics()
+        np.testing.assert_allclose(m["roll/baseline/mean"], base.mean(), rtol=1e-5)
+        np.testing.assert_allclose(m["roll/baseline/std"], base.std(), rtol=1e-4)
+        # remapped slicing keeps batch shapes stable and only returns valid samples
+        sl = col.slice_trajectories(traj, list(range(1024)))
+        np.testing.assert_array_equal(sl.returns.cpu().numpy(), traj.returns.cpu().numpy()[im])
+
+
+def test_evaluate_episodes_balanced_quotas():
+    from gymnasium_solver_b200.agents import build_agent
+
+    cfg = _cfg(n_envs=8, n_steps=32, batch_size=256, model_id="mlp_64x64", max_episode_steps=20)
+    agent = build_agent(cfg, rank=0, world_size=1)
+    col = agent.get_rollout_collector("val")
+    out = col.evaluate_episodes(n_episodes=21, deterministic=True)
+    assert out["cnt/total_episodes"] == 21
+    assert 1.0 <= out["roll/ep_len/mean"] <= 20.0 and out["roll/ep_rew/mean"] == out["roll/ep_len/mean"]
+    assert "action_dist" not in out and out["cnt/total_env_steps"] % (8 * 32) == 0
+
+
+@pytest.mark.parametrize("algo", ["ppo", "reinforce"])
+def test_losses_for_batch_on_reference_style_batches(golden_dir, algo):
+    """The reference's own calling convention: a gathered RolloutTrajectory of flat tensors -> {"loss", "early_stop_epoch"}."""
+    import os
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.rollout_buffer import RolloutTrajectory
+
+    d = np.load(os.path.join(golden_dir, "policy_cartpole64.npz"))
+    variant = "ppo" if algo == "ppo" else "reinforce"
+    cfg = _cfg("CartPole-v1", variant, n_envs=8, n_steps=12, batch_size=96, model_id="mlp_64x64", clip_range=0.2, ent_coef=0.01,
+               **({"normalize_advantages": "batch"} if algo == "ppo" else {}))
+    agent = build_agent(cfg, rank=0, world_size=1)
+    prefix = "p_" if algo == "ppo" else "rp_"
+    names = list(agent.policy_model.state_dict().keys())
+    sd = {n: torch.from_numpy(d[prefix + k]) for k, n in zip(OP.PARAM_ORDER, names) if prefix + k in d.files}
+    if algo == "reinforce":       # the engine's reinforce preset is actor-critic like the reference registry: zero the unused value head
+        sd.update({n: torch.zeros_like(agent.policy_model.state_dict()[n]) for n in names if n not in sd})
+    agent.policy_model.load_state_dict(sd)
+    t = lambda k, dt=torch.float32: torch.from_numpy(d[k]).to(dt)
+    batch = RolloutTrajectory(observations=t("obs"), actions=t("actions", torch.int64), rewards=torch.zeros(96), dones=torch.zeros(96, dtype=torch.bool),
+                              logprobs=t("old_logp" if algo == "ppo" else "r_old_logp"), values=t("values_old"), advantages=t("adv"),
+                              returns=t("ret"), next_observations=t("obs"))
+    res = agent.losses_for_batch(batch, 0)
+    assert set(res) == {"loss", "early_stop_epoch"} and res["early_stop_epoch"] is False
+    key = "ppo_batch" if algo == "ppo" else "rf_returns_off_off"
+    np.testing.assert_allclose(res["loss"].item(), float(d[f"{key}_loss"]), rtol=1e-4, atol=1e-6)
+    ref = np.concatenate([d[f"{key}_g_{k}"].ravel() for k in OP.PARAM_ORDER if f"{key}_g_{k}" in d.files])
+    g = agent.policy_model.flat_grads.cpu().numpy()[: ref.size]
+    np.testing.assert_allclose(g, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    # parameters' .grad are views of the flat buffer: torch optimizers see the kernel's gradients
+    np.testing.assert_array_equal(agent.policy_model.backbone[0].weight.grad.cpu().numpy().ravel(), g[:256])
+    agent._backpropagate_and_step(res["loss"])
+    m = agent.pop_epoch_metrics()
+    np.testing.assert_allclose(m["opt/loss/total"], float(d[f"{key}_loss"]), rtol=1e-4, atol=1e-6)
+    if algo == "ppo":
+        np.testing.assert_allclose(m["opt/grads/norm/all"], float(d["ppo_batch_m_opt/grads/norm/all"]), rtol=1e-4)
+
+
+def test_target_kl_early_stop_flag():
+    from gymnasium_solver_b200.agents import build_agent
+
+    cfg = _cfg(n_envs=8, n_steps=32, batch_size=256, model_id="mlp_64x64", target_kl=1e-9, policy_lr=0.01)
+    agent = build_agent(cfg, rank=0, world_size=1)
+    agent.train_one_rollout()   # after the first Adam step approx_kl > 1e-9 -> the remaining passes are skipped
+    assert agent._early_stop_epoch is True
+
+
+def test_cartpole_ppo_learns_on_the_reference_configuration():
+    """C1: CartPole-v1:ppo exactly as shipped (N=8, T=32, 256x256 MLP, 20 passes, 1e5 env steps).  The reference README
+    states this configuration solves CartPole (eval mean >= 475) inside the budget."""
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.random import set_random_seed
+
+    cfg = _cfg("CartPole-v1", "ppo")
+    set_random_seed(cfg.seed)
+    agent = build_agent(cfg, rank=0, world_size=1)
+    out = agent.learn()
+    hist = out["history"]
+    assert out["total_env_steps"] <= 1e5
+    train_curve = [r["train/roll/ep_rew/mean"] for r in hist if "train/roll/ep_rew/mean" in r]
+    assert max(train_curve) >= 195.0, f"train ep_rew mean peaked at {max(train_curve)}"
+    assert out["best_eval_reward"] >= 400.0, out["best_eval_reward"]
+    assert all(np.isfinite(r["train/opt/loss/total"]) for r in hist)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from gymnasium_solver_b200.agents import build_agent
+
+    cfg = _cfg(n_envs=8, n_steps=32, batch_size=256, model_id="mlp_64x64")
+    a = build_agent(cfg, rank=0, world_size=1)
+    a.train_one_rollout()
+    a.save_checkpoint(tmp_path / "ck")
+    b = build_agent(cfg, rank=0, world_size=1)
+    b.load_checkpoint(tmp_path / "ck")
+    assert torch.equal(a.policy_model.flat_params, b.policy_model.flat_params)
+    assert b.get_rollout_collector("train").total_steps == 256
+    assert set(torch.load(tmp_path / "ck" / "model.pt").keys()) == {"backbone.0.weight", "backbone.0.bias", "backbone.2.weight", "backbone.2.bias",
+                                                                   "policy_head.weight", "policy_head.bias", "value_head.weight", "value_head.bias"}

@@ -51,9 +51,9 @@ def _rollout_pair(env_id, n, steps, seed, max_episode_steps=None, wrappers=(), r
 
 @pytest.mark.parametrize("env_id", ENVS)
 def test_env_trajectories_match_oracle(env_id):
-    steps = {"CartPole-v1": 200, "Acrobot-v1": 120, "MountainCar-v0": 420}[env_id]
+    steps = {"CartPole-v1": 200, "Acrobot-v1": 520, "MountainCar-v0": 420}[env_id]
     n_done = _rollout_pair(env_id, 300, steps, seed=42)
-    assert n_done > 0  # autoreset / TimeLimit path exercised (CartPole terminates, MountainCar truncates at 200)
+    assert n_done > 0  # autoreset / TimeLimit path exercised (CartPole terminates, Acrobot truncates at 500, MountainCar at 200)
 
 
 @pytest.mark.parametrize("env_id", ENVS)

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""``python train.py <env>:<variant> [--override KEY=VALUE]... [--max-env-steps N]`` (reference: train.py:30-148).
+
+Multi-GPU: ``python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 train.py <env>:<variant>``; each
+rank owns n_envs/N environments and gradients are averaged over NCCL once per minibatch."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+
+def _parse_value(v: str):
+    low = v.lower()
+    if low in ("true", "false"):
+        return low == "true"
+    if low in ("none", "null"):
+        return None
+    for cast in (int, float):
+        try:
+            return cast(v)
+        except ValueError:
+            pass
+    try:
+        return json.loads(v)
+    except ValueError:
+        return v
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description="Train an agent on the b200 engine.")
+    ap.add_argument("config_id", nargs="?", default="CartPole-v1:ppo", help="<env>:<variant>, e.g. CartPole-v1:ppo")
+    ap.add_argument("--config_id", dest="config_id_opt", default=None)
+    ap.add_argument("--override", action="append", default=[], metavar="KEY=VALUE")
+    ap.add_argument("--max-env-steps", type=int, default=None)
+    ap.add_argument("--checkpoint-dir", default=None)
+    ap.add_argument("--resume", default=None, help="checkpoint directory to resume from")
+    args = ap.parse_args(argv)
+    spec = args.config_id_opt or args.config_id
+    if ":" not in spec:
+        ap.error("config must be <env>:<variant>")
+    env_id, variant = spec.split(":", 1)
+
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.config import load_config
+    from gymnasium_solver_b200.utils.random import set_random_seed
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    config = load_config(env_id, variant)
+    for ov in args.override:                      # applied after validation, like the reference (train_launcher.py:81-98)
+        k, _, v = ov.partition("=")
+        if not hasattr(config, k):
+            raise KeyError(f"unknown config key {k!r}")
+        setattr(config, k, _parse_value(v))
+    if args.max_env_steps is not None:
+        config.max_env_steps = args.max_env_steps
+    set_random_seed(config.seed)
+    agent = build_agent(config)
+    if args.resume:
+        agent.load_checkpoint(args.resume)
+
+    def log(row):
+        if config.quiet:
+            return
+        keys = ("epoch", "train/cnt/total_env_steps", "train/roll/ep_rew/mean", "train/roll/fps", "train/opt/loss/total",
+                "train/opt/ppo/approx_kl", "val/roll/ep_rew/mean")
+        print("  ".join(f"{k.split('/')[-1]}={row[k]:.4g}" if isinstance(row.get(k), float) else f"{k.split('/')[-1]}={row.get(k)}"
+                        for k in keys if k in row), flush=True)
+
+    result = agent.learn(log_fn=log)
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(f"Stopped: {result['stop_reason']}  epochs={result['epochs']}  env_steps={result['total_env_steps']}  "
+              f"elapsed={result['elapsed_s']:.1f}s  best_eval={result['best_eval_reward']}")
+        if args.checkpoint_dir:
+            agent.save_checkpoint(args.checkpoint_dir)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
