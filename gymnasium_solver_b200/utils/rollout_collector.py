@@ -44,7 +44,9 @@ class DeviceTrajectory:
                    "values": "values", "advantages": "adv", "returns": "ret", "next_observations": "next_obs"}[name]
             x = self.tm[src]
             if x is None:
-                raise N.EngineError(f"{name} was not stored for this rollout (store_next_obs=False)")
+                # not stored: with NEXT_STEP autoreset the observation returned by step t IS the policy input of step
+                # t+1, and the one after the last step is last_obs — rebuild it on demand, bit-identical
+                x = torch.cat([self.tm["obs"][1:], self.tm["last_obs"][None]], dim=0)
             y = _env_major(x)
             if name == "actions":
                 y = y.to(torch.int64)
@@ -261,7 +263,7 @@ class RolloutCollector:
         sl = slice(start, end)
         tm = dict(obs=b.obs_buf[sl], next_obs=None if b.next_obs_buf is None else b.next_obs_buf[sl], actions=b.actions_buf[sl],
                   rewards=b.rewards_buf[sl], dones=b.dones_buf[sl], timeouts=b.timeouts_buf[sl], logprobs=b.logprobs_buf[sl],
-                  values=b.values_buf[sl], adv=adv, ret=ret, idx_map=self._last_rollout_index_map)
+                  values=b.values_buf[sl], adv=adv, ret=ret, idx_map=self._last_rollout_index_map, last_obs=self._last_obs)
         self.total_rollouts += 1
         return DeviceTrajectory(tm, self.n_steps, self.n_envs)
 
