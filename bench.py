@@ -188,7 +188,12 @@ def run_b200(args):
     e2e_value = steps_per_iter_local * world * e2e_steps / float(e2e_s.item())
 
     # ---- roofline of the dominant kernel (the fused update kernel), timed alone on its own stream ----------------------
-    roof = kernel_rooflines(agent, cfg, dev) if rank == 0 else None
+    # (rank 0 only, with the collectives switched off: the microbench must not enter all-reduces the other ranks never join)
+    roof = None
+    if rank == 0:
+        agent.world_size = 1
+        roof = kernel_rooflines(agent, cfg, dev)
+        agent.world_size = world
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args, threads=1, budget_s=20.0)
@@ -217,6 +222,7 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

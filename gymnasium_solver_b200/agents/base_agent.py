@@ -29,6 +29,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as N
+from ..utils.distributed import average_gradients, shard_spec
 from ..utils.environment import build_env_from_config
 from ..utils.optimizer_factory import build_optimizer
 from ..utils.policy_factory import build_policy_from_env_and_config
@@ -128,12 +129,8 @@ class BaseAgent(nn.Module):
         self.n_epochs = config.n_epochs
         self.metrics_recorder = MetricsRecorder()
 
-        if int(config.n_envs) % self.world_size != 0:
-            raise ValueError(f"n_envs={config.n_envs} must be divisible by world_size={self.world_size}")
-        if int(config.batch_size) % self.world_size != 0:
-            raise ValueError(f"batch_size={config.batch_size} must be divisible by world_size={self.world_size}")
-        self.local_n_envs = int(config.n_envs) // self.world_size
-        self.local_batch_size = int(config.batch_size) // self.world_size
+        self.shard = shard_spec(int(config.n_envs), int(config.batch_size), self.rank, self.world_size)
+        self.local_n_envs, self.local_batch_size = self.shard.n_envs, self.shard.batch_size
 
         for stage in STAGES:
             self.build_env(stage)
@@ -158,7 +155,7 @@ class BaseAgent(nn.Module):
         seed = {"train": cfg.seed_train, "val": cfg.seed_val, "test": cfg.seed_test}[stage]
         with torch.cuda.device(self.device):
             env = build_env_from_config(cfg, seed=seed, n_envs=self.local_n_envs, device=self.device,
-                                        env_id_offset=self.rank * self.local_n_envs, **kwargs)
+                                        env_id_offset=self.shard.env_id_offset, **kwargs)
         self._envs[stage] = env
         return env
 
@@ -244,8 +241,7 @@ class BaseAgent(nn.Module):
         The gradients were produced by the fused kernel; with several ranks they are averaged over NVLink first."""
         opt = self.optimizers()
         model = self.policy_model
-        if self.world_size > 1:
-            torch.distributed.all_reduce(model.flat_grads, op=torch.distributed.ReduceOp.AVG)
+        average_gradients(model.flat_grads, self.world_size)
         mlp = N.mlp_struct(model)
         max_norm = float(self.config.max_grad_norm) if self.config.max_grad_norm is not None else 0.0
         with torch.cuda.device(self.device):

@@ -11,6 +11,7 @@ import ctypes as C
 import torch
 
 from ... import _native as N
+from ...utils.distributed import allreduce_moments
 from ..base_agent import BaseAgent, EngineLoss
 
 
@@ -36,8 +37,7 @@ class PPOAgent(BaseAgent):
             if hp.normalize_adv:
                 self._adv_mom.zero_()
                 N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._adv_mom), st))
-                if self.world_size > 1:      # "batch" statistics are those of the GLOBAL minibatch (W-invariant update)
-                    torch.distributed.all_reduce(self._adv_mom)
+                allreduce_moments(self._adv_mom, self.world_size)   # statistics of the GLOBAL minibatch (W-invariant update)
             N.check(L.gs_ppo_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(self._adv_mom), N.ptr(model.flat_grads),
                                   N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
         early_stop = False

@@ -10,6 +10,7 @@ import ctypes as C
 import torch
 
 from ... import _native as N
+from ...utils.distributed import allreduce_moments
 from ..base_agent import BaseAgent, EngineLoss
 
 
@@ -40,8 +41,7 @@ class REINFORCEAgent(BaseAgent):
                     N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.ret, N.ptr(self._mom[0]), st))
                 if hp.normalize_adv:
                     N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._mom[1]), st))
-                if self.world_size > 1:
-                    torch.distributed.all_reduce(self._mom)
+                allreduce_moments(self._mom, self.world_size)
             N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(self._mom[0]), N.ptr(self._mom[1]),
                                         N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
         return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=False)

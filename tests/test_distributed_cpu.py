@@ -1,0 +1,63 @@
+"""World-size-2 gloo tests (CPU) of the data-parallel host logic: env sharding arithmetic, gradient averaging and global
+minibatch moments.  The kernels themselves are exercised on the GPU box; this covers the N > 1 plumbing."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gymnasium_solver_b200.utils.distributed import allreduce_moments, average_gradients, max_over_ranks, shard_spec
+
+
+def test_shard_spec_partitions_envs_and_batches():
+    shards = [shard_spec(65536 * 8, 1048576 * 8, r, 8) for r in range(8)]
+    assert [s.env_id_offset for s in shards] == [r * 65536 for r in range(8)]
+    assert all(s.n_envs == 65536 and s.batch_size == 1048576 for s in shards)
+    assert sum(s.n_envs for s in shards) == 65536 * 8
+    with pytest.raises(ValueError):
+        shard_spec(10, 8, 0, 4)
+    with pytest.raises(ValueError):
+        shard_spec(8, 10, 0, 4)
+    with pytest.raises(ValueError):
+        shard_spec(8, 8, 4, 4)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        grads = torch.randn(4675, generator=g)
+        local = grads.clone()
+        average_gradients(grads, world)
+        # per-rank (sum, sumsq, count) of that rank's minibatch shard -> global moments
+        x = torch.randn(1000 + 10 * rank, generator=g, dtype=torch.float64)
+        mom = torch.tensor([x.sum(), (x * x).sum(), float(x.numel())], dtype=torch.float64)
+        allreduce_moments(mom, world)
+        t = max_over_ranks(1.0 + rank, torch.device("cpu"), world)
+        out.put((rank, local.numpy(), grads.numpy(), x.numpy(), mom.numpy(), t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_average_and_global_moments_world2():
+    world, port = 2, 29500 + os.getpid() % 1000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mean = (res[0][1] + res[1][1]) / 2
+    for r in res:
+        np.testing.assert_allclose(r[2], mean, rtol=1e-6, atol=1e-7)       # every rank holds the same averaged gradient
+    np.testing.assert_array_equal(res[0][2], res[1][2])                      # bit-identical -> identical optimizer steps
+    allx = np.concatenate([res[0][3], res[1][3]])
+    for r in res:
+        np.testing.assert_allclose(r[4], [allx.sum(), (allx ** 2).sum(), allx.size], rtol=1e-12)
+        assert r[5] == 2.0
