@@ -5,62 +5,20 @@
 //           PPOAgent.losses_for_batch (agents/ppo/ppo_agent.py:21-152), REINFORCEAgent.losses_for_batch
 //           (agents/reinforce/reinforce_agent.py:11-88), loss.backward(), BaseModel activation hooks
 //           (utils/models.py:121-194), compute_grad_norms + clip_gradients (agents/base_agent.py:591-621).
+#include <stdlib.h>
+#include <string.h>
+
 #include "mlp_tile.cuh"
+#include "update_shared.cuh"
 
 namespace gs {
-
-enum { ALGO_PPO = 0, ALGO_REINFORCE = 1 };
-
-// per-CTA partial sums (doubles)
-enum {
-    PM_SURR = 0, PM_VLOSS, PM_ENT, PM_CLIPF, PM_CLIPF_VF, PM_RV, PM_RV2, PM_R, PM_R2, PM_KL, PM_AKL, PM_ADVN, PM_ADVN2,
-    PM_TGT, PM_TGT2, PM_RETN, PM_RETN2, PM_Z0, PM_Z0SQ, PM_Z1, PM_Z1SQ, PM_COUNT, PM_N
-};
-
-struct BatchDev {
-    int64_t n;
-    const int64_t* idx;
-    uint64_t perm_key;
-    int64_t perm_offset, perm_len;
-    const int64_t* idx_map;
-    int T, D;
-    int64_t N;
-    const float* obs;
-    const int32_t* actions;
-    const float *logp_old, *values_old, *adv, *ret;
-};
-
-struct HpDev {
-    float clip_lo, clip_hi, clip_vf, vf_coef, ent_coef;
-    int normalize_adv, normalize_ret, policy_targets;
-};
-
-__device__ __forceinline__ int64_t sample_offset(const BatchDev& b, int64_t pos) {
-    int64_t i;
-    if (b.idx) i = b.idx[pos];
-    else if (b.perm_len > 0) i = (int64_t)feistel_permute((uint64_t)(b.perm_offset + pos), (uint64_t)b.perm_len, b.perm_key);
-    else i = b.perm_offset + pos;
-    if (b.idx_map) i = b.idx_map[i];
-    const int64_t e = i / b.T, t = i - e * b.T;   // env-major id -> (env, step)
-    return t * b.N + e;                            // time-major offset
-}
-
-// mean / (std + eps) denominators from raw moments {sum, sumsq, count}; unbiased std like torch.std
-__device__ __forceinline__ void norm_consts(const double* mom, float& mean, float& denom) {
-    const double n = mom[2];
-    const double mu = mom[0] / n;
-    double var = (mom[1] - mom[0] * mu) / (n - 1.0);
-    var = var > 0.0 ? var : 0.0;
-    mean = (float)mu;
-    denom = (float)sqrt(var) + 1e-8f;
-}
 
 // ---- the fused kernel -----------------------------------------------------------------------------------------------
 template <class C, int ALGO, bool TRACK>
 __global__ void __launch_bounds__(kThreads, (C::kSmemFloats * 4 <= 110 * 1024) ? 2 : 1)
 update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom, const double* __restrict__ ret_mom,
               float* __restrict__ grad_partials /* persist: [grid][P] */, float* __restrict__ grads_atomic /* else: [P] */,
-              double* __restrict__ metric_partials /* [grid][PM_N] */, uint32_t* __restrict__ dead) {
+              double* __restrict__ metric_partials /* [grid][PM_N] */, uint32_t* __restrict__ dead, int64_t pstride) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -146,61 +104,7 @@ update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom
             if (tid < valid_rows) {
                 float out[kNH];
                 forward_heads<C>(sm, tid, out);
-                const int A = m.A;
-                float lp[3] = {0.f, 0.f, 0.f}, p[3] = {0.f, 0.f, 0.f};
-                log_softmax(out, A, lp);
-                float H = 0.f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k < A) { p[k] = expf(lp[k]); H -= p[k] * lp[k]; }
-                const float logp = a_s == 0 ? lp[0] : (a_s == 1 ? lp[1] : lp[2]);
-                float dlogp;
-                if (ALGO == ALGO_PPO) {
-                    const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
-                    const float ratio = expf(logp - lp_old);
-                    const float rc = fminf(fmaxf(ratio, hp.clip_lo), hp.clip_hi);
-                    const float s1 = adv_n * ratio, s2 = adv_n * rc;
-                    const bool inrange = (ratio >= hp.clip_lo) && (ratio <= hp.clip_hi);
-                    dlogp = (inrange || s1 < s2) ? -(s1 * invB) : 0.f;
-                    pm[PM_SURR] += fminf(s1, s2);
-                    pm[PM_CLIPF] += inrange ? 0.f : 1.f;
-                    pm[PM_ADVN] += adv_n; pm[PM_ADVN2] = fmaf(adv_n, adv_n, pm[PM_ADVN2]);
-                    // clipped value loss
-                    const float v = A == 2 ? out[2] : out[3];
-                    const float vd = v - v_old;
-                    const float eu = v - ret_s, lu = eu * eu;
-                    const float vc = v_old + fminf(fmaxf(vd, -hp.clip_vf), hp.clip_vf);
-                    const float ec = vc - ret_s, lc = ec * ec;
-                    const bool in_vf = (vd >= -hp.clip_vf) && (vd <= hp.clip_vf);
-                    const float gc = in_vf ? 2.f * ec : 0.f;
-                    const float dv = lu > lc ? 2.f * eu : (lu < lc ? gc : 0.5f * (2.f * eu) + 0.5f * gc);
-                    const float gv = hp.vf_coef * dv * invB;
-                    if (A == 2) g[2] = gv; else g[3] = gv;
-                    pm[PM_VLOSS] += fmaxf(lu, lc);
-                    pm[PM_CLIPF_VF] += in_vf ? 0.f : 1.f;
-                    const float rv = ret_s - v;
-                    pm[PM_RV] += rv; pm[PM_RV2] = fmaf(rv, rv, pm[PM_RV2]);
-                    pm[PM_R] += ret_s; pm[PM_R2] = fmaf(ret_s, ret_s, pm[PM_R2]);
-                } else {
-                    const float ret_n = hp.normalize_ret ? (ret_s - ret_mean) / ret_den : ret_s;
-                    const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
-                    const float tgt = hp.policy_targets == 0 ? ret_n : adv_n;
-                    dlogp = -(tgt * invB);
-                    pm[PM_SURR] += logp * tgt;
-                    pm[PM_TGT] += tgt; pm[PM_TGT2] = fmaf(tgt, tgt, pm[PM_TGT2]);
-                    pm[PM_ADVN] += adv_n; pm[PM_ADVN2] = fmaf(adv_n, adv_n, pm[PM_ADVN2]);
-                    pm[PM_RETN] += ret_n; pm[PM_RETN2] = fmaf(ret_n, ret_n, pm[PM_RETN2]);
-                }
-                const float ec_b = hp.ent_coef * invB;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k < A) g[k] = dlogp * ((k == a_s ? 1.f : 0.f) - p[k]) + ec_b * p[k] * (lp[k] + H);
-                pm[PM_ENT] += H;
-                pm[PM_KL] += lp_old - logp;
-                const float dcl = fminf(fmaxf(logp - lp_old, -20.f), 20.f);   // utils/torch.py:115-118
-                const float r2 = expf(dcl);
-                pm[PM_AKL] += (r2 - 1.f) - logf(r2);
-                pm[PM_COUNT] += 1.f;
+                sample_loss<ALGO>(out, m.A, a_s, lp_old, v_old, adv_s, ret_s, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm);
             }
             *reinterpret_cast<float4*>(sm + C::oG + tid * kNH) = make_float4(g[0], g[1], g[2], g[3]);
         }
@@ -386,7 +290,7 @@ update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom
             else if (tid == m.A && m.has_value) gsm[po.bv] = acc_bh;
         }
         __syncthreads();
-        float* out = grad_partials + (size_t)blockIdx.x * P;
+        float* out = grad_partials + (size_t)blockIdx.x * pstride;
         for (int i = tid; i < P; i += kThreads) out[i] = gsm[i];
     }
 
@@ -412,11 +316,11 @@ update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom
 }
 
 // ---- stage 2: ordered reduction over CTAs + metric finalisation ---------------------------------------------------------
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int64_t P, float* __restrict__ grads) {
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int64_t P, int64_t pstride, float* __restrict__ grads) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * P + i];
+    for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * pstride + i];
     grads[i] = s;
 }
 
@@ -597,7 +501,7 @@ static int64_t ws_bytes(const gs_mlp_t* m, int device) {
     const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
     const int grid = update_grid(device);
     int64_t b = 0;
-    b += ((int64_t)grid * P * 4 + 255) / 256 * 256;
+    b += ((int64_t)grid * ((P + 3) & ~3ll) * 4 + 255) / 256 * 256;
     b += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
     b += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
     b += 256;
@@ -608,11 +512,26 @@ static UpdateWs carve(void* ws, const gs_mlp_t* m, int grid) {
     const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
     char* p = (char*)ws;
     UpdateWs w;
-    w.grad_partials = (float*)p; p += ((int64_t)grid * P * 4 + 255) / 256 * 256;
+    w.grad_partials = (float*)p; p += ((int64_t)grid * ((P + 3) & ~3ll) * 4 + 255) / 256 * 256;
     w.metric_partials = (double*)p; p += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
     w.dead = (uint32_t*)p; p += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
     w.sq = (double*)p;
     return w;
+}
+
+// tensor-core kernel of update_tc.cu (64x64 networks)
+template <int ALGO>
+int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
+                     float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid, cudaStream_t st);
+
+// 0 = tensor cores where a kernel exists (64x64), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
+static int g_update_impl = -1;
+static int update_impl() {
+    if (g_update_impl < 0) {
+        const char* e = getenv("GS_UPDATE_IMPL");
+        g_update_impl = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+    }
+    return g_update_impl;
 }
 
 template <class C, int ALGO>
@@ -624,18 +543,28 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     const UpdateWs w = carve(ws, m, grid_max);
     const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
     const size_t smem = (size_t)C::kSmemFloats * sizeof(float);
+    const int64_t pstride = (P + 3) & ~3ll;   // 16-byte aligned partial vectors
     const MlpDev md = to_dev(m);
     if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)(m->hidden1 + m->hidden2) * 4, st));
     if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
-    auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
-    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(md, b, hp, adv_mom, ret_mom, w.grad_partials, grads_flat, w.metric_partials, w.dead);
-    GS_LAUNCH_CHECK();
-    if (C::kPersist) {
-        reduce_partials_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.grad_partials, grid, P, grads_flat);
+    int n_partials = grid;
+    if (C::H1 == 64 && C::H2 == 64 && update_impl() == 0) {
+        const int64_t tiles128 = (b.n + 127) / 128;
+        const int sms = sm_count(device);
+        n_partials = (int)(tiles128 < sms ? tiles128 : sms);
+        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
+    } else {
+        auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
+        GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, st>>>(md, b, hp, adv_mom, ret_mom, w.grad_partials, grads_flat, w.metric_partials, w.dead, pstride);
         GS_LAUNCH_CHECK();
     }
-    finalize_metrics_kernel<<<1, 64, 0, st>>>(w.metric_partials, grid, ALGO, m->hidden1, m->hidden2, track ? 1 : 0, hp.vf_coef,
+    const int grid_used = n_partials;
+    if (C::kPersist) {
+        reduce_partials_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.grad_partials, grid_used, P, pstride, grads_flat);
+        GS_LAUNCH_CHECK();
+    }
+    finalize_metrics_kernel<<<1, 64, 0, st>>>(w.metric_partials, grid_used, ALGO, m->hidden1, m->hidden2, track ? 1 : 0, hp.vf_coef,
                                               hp.ent_coef, hp.normalize_adv, hp.normalize_ret, w.dead, metrics);
     GS_LAUNCH_CHECK();
     return 0;
@@ -674,6 +603,12 @@ static BatchDev to_dev(const gs_batch_t* b) {
 using namespace gs;
 
 extern "C" {
+
+int gs_set_update_impl(int impl) {
+    if (impl != 0 && impl != 1) GS_FAIL("gs_set_update_impl: 0 = tensor cores where available, 1 = fp32 SIMT");
+    g_update_impl = impl;
+    return 0;
+}
 
 int64_t gs_mlp_param_count(const gs_mlp_t* m) {
     if (validate_mlp(m)) return -1;
