@@ -96,7 +96,7 @@ SIGNATURES = {
     "gs_normalize": (_i32, [_vp, _i64, _vp, _f32, _vp, _vp]),
     "gs_shift_by_mean": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "gs_batch_moments": (_i32, [C.POINTER(GsBatch), _vp, _vp, _vp]),
-    "gs_update_workspace_bytes": (_i64, [C.POINTER(GsMlp), _i32]),
+    "gs_update_workspace_bytes": (_i64, [C.POINTER(GsMlp), _i32, _i64]),
     "gs_set_update_impl": (_i32, [_i32]),
     "gs_mlp_param_count": (_i64, [C.POINTER(GsMlp)]),
     "gs_ppo_step": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), C.POINTER(GsPpoHparams), _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -140,7 +140,7 @@ class BaseAgent(nn.Module):
 
         # device scratch of the update path
         mlp = N.mlp_struct(self.policy_model)
-        self._ws_bytes = N.lib().gs_update_workspace_bytes(C.byref(mlp), self.device.index)
+        self._ws_bytes = N.lib().gs_update_workspace_bytes(C.byref(mlp), self.device.index, int(self.local_batch_size))
         if self._ws_bytes <= 0:
             raise N.EngineError(N.lib().gs_last_error().decode())
         self._workspace = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)

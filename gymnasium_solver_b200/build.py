@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("GS_NVCC_EXTRA", "").split(), "-c", s, "-o", o]   # e.g. -DGS_TC_TRACE
             if verbose:
                 print(" ".join(cmd), flush=True)
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -60,6 +60,23 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- single-thread issue --------------------------------------------------------------------------------------------------
+// tcgen05.mma / commit take their operands from UNIFORM registers.  Issued under a thread-dependent branch (tid == 0) the
+// compiler wraps every MMA in an ELECT / R2UR / BRA.U.ANY loop (~11 instructions and two uniform-datapath round trips
+// each); under a warp-uniform branch + elect.sync, with operands derived from warp-uniform values, it is one UTCHMMA.
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA -------------------------------------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -129,6 +146,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                  "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -140,9 +162,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // round-to-nearest tf32 split: hi = rn_tf32(x) (cvt.rna), lo = x - hi is exact, signed and <= 2^-12 |x|; the tensor core
 // then truncates lo to 11 bits, so a product hi*hi + lo*hi + hi*lo carries ~2^-23 relative error (fp32-like, unbiased)
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    // round-half-away on the 13 dropped mantissa bits, two integer ops (cvt.rna.tf32.f32 costs four: it guards inf / nan,
+    // which never reach an operand here)
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 }  // namespace tc

@@ -493,11 +493,12 @@ struct UpdateWs {  // workspace carve-up
     double* metric_partials;
     uint32_t* dead;
     double* sq;
+    uint32_t* offs;   // time-major offset of every minibatch sample (gather_offsets_kernel), max_batch entries
 };
 
 static int update_grid(int device) { return 2 * sm_count(device); }
 
-static int64_t ws_bytes(const gs_mlp_t* m, int device) {
+static int64_t ws_bytes(const gs_mlp_t* m, int device, int64_t max_batch) {
     const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
     const int grid = update_grid(device);
     int64_t b = 0;
@@ -505,6 +506,7 @@ static int64_t ws_bytes(const gs_mlp_t* m, int device) {
     b += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
     b += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
     b += 256;
+    b += (max_batch * 4 + 255) / 256 * 256;
     return b;
 }
 
@@ -515,14 +517,24 @@ static UpdateWs carve(void* ws, const gs_mlp_t* m, int grid) {
     w.grad_partials = (float*)p; p += ((int64_t)grid * ((P + 3) & ~3ll) * 4 + 255) / 256 * 256;
     w.metric_partials = (double*)p; p += ((int64_t)grid * PM_N * 8 + 255) / 256 * 256;
     w.dead = (uint32_t*)p; p += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
-    w.sq = (double*)p;
+    w.sq = (double*)p; p += 256;
+    w.offs = (uint32_t*)p;
     return w;
 }
 
 // tensor-core kernel of update_tc.cu (64x64 networks)
 template <int ALGO>
 int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
-                     float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid, cudaStream_t st);
+                     const uint32_t* offs, float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid,
+                     cudaStream_t st);
+
+// Sample-id translation of the whole minibatch in one pass: offs[pos] = time-major offset of minibatch position pos.  The
+// keyed Feistel walk + env-major -> time-major division is a ~1000-instruction dependent chain per sample (cycle walking
+// diverges inside a warp); done here it is spread over the whole GPU instead of sitting on the update kernel's critical path.
+__global__ void gather_offsets_kernel(BatchDev b, uint32_t* __restrict__ offs) {
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos < b.n) offs[pos] = (uint32_t)sample_offset(b, pos);
+}
 
 // 0 = tensor cores where a kernel exists (64x64), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
 static int g_update_impl = -1;
@@ -548,11 +560,13 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)(m->hidden1 + m->hidden2) * 4, st));
     if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
     int n_partials = grid;
-    if (C::H1 == 64 && C::H2 == 64 && update_impl() == 0) {
+    if (C::H1 == 64 && C::H2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32)) {
+        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs);
+        GS_LAUNCH_CHECK();
         const int64_t tiles128 = (b.n + 127) / 128;
         const int sms = sm_count(device);
         n_partials = (int)(tiles128 < sms ? tiles128 : sms);
-        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
+        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, w.offs, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
     } else {
         auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
         GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -576,8 +590,10 @@ static int launch_update(const gs_mlp_t* m, const BatchDev& b, const HpDev& hp, 
     if (validate_mlp(m)) return -1;
     int device = 0;
     GS_CUDA(cudaGetDevice(&device));
-    if (ws_size < ws_bytes(m, device)) GS_FAIL("workspace too small: %lld < %lld", (long long)ws_size, (long long)ws_bytes(m, device));
     if (b.n <= 0) GS_FAIL("empty minibatch");
+    if (ws_size < ws_bytes(m, device, b.n))
+        GS_FAIL("workspace too small for a %lld-sample minibatch: %lld < %lld (gs_update_workspace_bytes)", (long long)b.n, (long long)ws_size,
+                (long long)ws_bytes(m, device, b.n));
     if (b.D != m->obs_dim) GS_FAIL("batch obs_dim %d != mlp obs_dim %d", b.D, m->obs_dim);
     const int h1 = m->hidden1, h2 = m->hidden2;
 #define GS_DISPATCH(H1, H2, S) \
@@ -615,9 +631,10 @@ int64_t gs_mlp_param_count(const gs_mlp_t* m) {
     return mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
 }
 
-int64_t gs_update_workspace_bytes(const gs_mlp_t* m, int device) {
+int64_t gs_update_workspace_bytes(const gs_mlp_t* m, int device, int64_t max_batch) {
     if (validate_mlp(m)) return -1;
-    return ws_bytes(m, device);
+    if (max_batch < 0) GS_FAIL("gs_update_workspace_bytes: negative max_batch");
+    return ws_bytes(m, device, max_batch);
 }
 
 int gs_batch_moments(const gs_batch_t* batch, const float* field, double* out, void* stream) {

@@ -1,22 +1,41 @@
 // update_tc.cu — tcgen05 / TMEM version of the fused minibatch update for the 64x64 MLP (PPO and REINFORCE).
 //
 // Same contract as update_kernels.cu::update_kernel (gather -> forward -> loss + metrics -> backward -> per-CTA partial
-// gradients), but the three 64x64 GEMMs and every cross-sample reduction run on the 5th-gen tensor cores:
+// gradients), but the 64x64 GEMMs and every cross-sample reduction run on the 5th-gen tensor cores.  Four MMA groups per
+// 128-sample tile (3xTF32: hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM):
 //
-//   forward  z2[s][j]   = sum_k h1[s][k]  W2[j][k]        M=128 (samples)  N=64  K=64   A: TMEM (h1 rows),  B: W2   smem
-//   dgrad    dh1[s][k]  = sum_j dz2[s][j] W2[j][k]        M=128            N=64  K=64   A: TMEM (dz2 rows), B: W2^T smem
-//   wgrad    dW2[j][k] += sum_s dz2[s][j] h1[s][k]        M=64   N=64  K=128 (samples)  A: dz2^T smem, B: h1^T smem
-//   heads    dWh[r][k] += sum_s g[s][r]   h2[s][k]        M=64 (k)  N=8 (r)  K=128      A: h2^T  smem, B: g^T  smem
-//   layer 1  dW1[j][d] += sum_s dz1[s][j] x[s][d], db1    M=64   N=8 (d, col 7 = ones)  A: dz1^T smem, B: x^T  smem
-//   bias 2   db2[j]    += sum_s dz2[s][j]                 M=64   N=8 (col 7 = ones)     A: dz2^T smem, B: x^T  smem
+//   fwd(u)    z2[s][j]   = sum_k h1[s][k]  W2[j][k]      M=128 (samples) N=64 K=64    A: TMEM (h1 rows),  B: W2   smem
+//   dgrad(t)  dh1[s][k]  = sum_j dz2[s][j] W2[j][k]      M=128           N=64 K=64    A: TMEM (dz2 rows), B: W2^T smem
+//   dW2(t)    dW2[j][k] += sum_s dz2[s][j] h1[s][k]      M=64  N=72 K=128 (samples)   A: dz2^T (P), B: h1^T + a ones row (S):
+//             db2[j]    += sum_s dz2[s][j]                                             column 64 of the same accumulator
+//   tail(t,u) dW1[j][d] += sum_s dz1(t)[s][j] x(t)[s][d], db1 (ones row of x^T)        M=128 N=16 K=128
+//             dWh[r][k] += sum_s g(u)[s][r] h2(u)[s][k]                                A: [dz1^T(t) ; h2^T(u)] (P;S), B: [x^T(t) ; g^T(u)]
+//             (one MMA group, block-diagonal use of a 128x16 accumulator; the off-diagonal blocks are never read)
 //
-// Precision: every product is a 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM): ~1.5e-6 relative,
-// measured on hardware by csrc/probes/tc_probe.cu, which keeps the 1e-4 gradient parity bar of the fp32 path.
-// Layer 1, heads, softmax, loss and the activation derivatives are row-local fp32 SIMT work on registers; wgrad accumulators live in TMEM and are folded into fp32 partials every kFlushTiles tiles.
-// All shared-memory operands use the K-major SWIZZLE_128B slab layout of tc_common.cuh (the only layout tf32 needs here);
-// transposed copies ([feature][sample]) are written straight from registers, conflict-free (a warp writes 128 contiguous
-// bytes of one row).  1 CTA of 512 threads per SM (thread = sample row x 16-column chunk), 225 KB shared memory, all 512 TMEM
-// columns; MMA groups are issued by four different warps (one accumulator each, so every accumulation order is fixed).
+// Layer 1, heads, softmax, loss and the activation derivatives are row-local fp32 SIMT work on registers.  Shared-memory
+// operands use the K-major SWIZZLE_128B slab layout of tc_common.cuh; the transposed operands ([feature][sample]) are
+// written straight from registers, conflict-free (a warp writes 128 contiguous bytes of one row).  P and S are the two
+// 64-row halves of ONE 128-row tile (+ 8 rows holding the ones row behind S), so the same bytes serve as M=64 / N=72
+// operands of dW2 and as the M=128 operand of the tail group.
+//
+// Schedule: 1 CTA of 512 threads per SM (thread = sample row x 16-column chunk), 216 KB shared memory, all 512 TMEM columns.
+// The loop is software-pipelined over tiles: iteration `it` runs the BACKWARD phase of tile t and the FORWARD phase of the
+// next tile u in one instruction stream, so every MMA group has independent SIMT work behind it:
+//
+//   B1(t)  z2 -> dz2 -> TMEM A[cur] ; wait tail(t-1) ; dz2^T -> P, h1^T -> S, x^T(t) -> Y    | owners: sample(u) -> TMEM scratch
+//   ---- sync 1 ----   issue dgrad(t) [A[cur] -> acc[cur]], dW2(t) [P,S]
+//   F1(u)  layer 1 -> h1(u) -> TMEM A[nxt]
+//   ---- sync 2 ----   issue fwd(u) [A[nxt] -> acc[nxt]]
+//   F2(u)  wait fwd(u); z2 -> h2 -> partial head outputs -> TMEM scratch
+//   ---- sync 3 ----
+//   F3(u)  loss, d(loss)/d(heads) -> g (every chunk thread of the row; metrics by the row owner), g^T(u) -> Y
+//          wait dgrad(t), dW2(t) ; dz1^T(t) -> P, h2^T(u) -> S
+//   ---- sync 4 ----   issue tail(t,u) [P;S, Y]
+//
+// TMEM A operands and the z2 / dh1 accumulator are double-buffered (cur/nxt); the transposed operand tile is single
+// (shared memory is the limit).  Per-row exchanges between the four chunk threads of a row (head partial sums, gathered
+// sample) go through spare TMEM columns: all four warps of a quadrant address the same lanes.  Each MMA group is issued by
+// one warp (elect.sync), one accumulator each, so every accumulation order is fixed (deterministic).
 #include <type_traits>
 
 #include "mlp_tile.cuh"
@@ -30,50 +49,60 @@ using namespace tc;
 namespace tcu {
 constexpr int kRows = 128;              // samples per tile == TMEM lanes
 constexpr int kT = 512;                 // threads: thread = (row, 16-column chunk); warp w -> rows 32*(w&3).., chunk w>>2
-// shared memory map (bytes)
-constexpr int oQ = 0;                   // h1^T then dz1^T   hi [0,32K) lo [32K,64K)     [64 rows][128 samples]
-constexpr int oR = 65536;               // h2^T then dz2^T
-constexpr int oW2 = 131072;             // W2  hi 16K, lo 16K      [64 j][64 k]
-constexpr int oW2T = 163840;            // W2^T                    [64 k][64 j]
-constexpr int oGT = 196608;             // g^T  hi 4K, lo 4K       [8 r][128 samples]
-constexpr int oXT = 204800;             // x^T  hi 4K, lo 4K       [8 d][128 samples], row 7 = ones
-constexpr int oMisc = 212992;
+// shared memory map (bytes).  Transposed operand tile: 4 slabs (32 samples each) x rows x 128 B.
+constexpr int kHiRows = 136;            // P rows 0..63, S rows 64..127, ones row 128 (+7 zero rows: N is a multiple of 8)
+constexpr int kHiSlab = kHiRows * 128;  // 17408 B
+constexpr int kLoSlab = 128 * 128;      // 16384 B (no ones rows: their lo part is 0, that pass runs with N=64)
+constexpr int oTH = 0;                  // hi tile  [4][136][32] fp32
+constexpr int oTL = 4 * kHiSlab;        // lo tile  [4][128][32] fp32
+constexpr int oW2 = oTL + 4 * kLoSlab;  // W2  hi 16K, lo 16K      [64 j][64 k]
+constexpr int oW2T = oW2 + 32768;       // W2^T                    [64 k][64 j]
+constexpr int oY = oW2T + 32768;        // [x^T ; g^T]: hi 8K, lo 8K   [16 rows][128 samples]; row 7 = ones, rows 8.. = g^T
+constexpr int oMisc = oY + 16384;
 constexpr int oW1 = oMisc;              // [64][8] fp32
 constexpr int oB1 = oW1 + 2048;
 constexpr int oB2 = oB1 + 256;
 constexpr int oWH = oB2 + 256;          // [4][64]
 constexpr int oBH = oWH + 1024;         // [4]
-constexpr int oBar = oBH + 16;          // 5 mbarriers
+constexpr int oBar = oBH + 16;          // 4 mbarriers
 constexpr int oTmem = oBar + 64;
 constexpr int oRed = oTmem + 16;        // PM_N doubles + 4 floats (block reductions through shared atomics)
-constexpr int oOutP = oRed + 256;       // partial head outputs [4 chunks][128 rows] float4
-constexpr int kSmemBytes = oOutP + 4 * 128 * 16;
+constexpr int kSmemBytes = oRed + 256;
+static_assert(oTL % 1024 == 0 && oW2 % 1024 == 0 && oY % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
-// TMEM columns
-constexpr uint32_t cAhi = 0, cAlo = 64, cAcc = 128, cW2 = 192, cWH = 256, cW1 = 264, cB2 = 272, kTmemCols = 512;
-enum { BAR_FWD = 0, BAR_H, BAR_D, BAR_W, BAR_1 };
+// TMEM columns: A[b] = 128*b (hi +0, lo +64); acc[b] = 256 + 64*b; dW2|db2 (72 used of 80); tail accumulator; per-row scratch
+constexpr uint32_t cA = 0, cAcc = 256, cW2 = 384, cC = 464, cOP = 480, cSX = 496, kTmemCols = 512;
+enum { BAR_FWD = 0, BAR_D, BAR_W, BAR_T };
 }  // namespace tcu
+
+// Development aid (build with GS_NVCC_EXTRA=-DGS_TC_TRACE): per-warp clock64() stamps of one pipeline iteration of one CTA,
+// read back with gs_debug_tc_trace().  Not part of the ABI; absent from normal builds.
+#ifdef GS_TC_TRACE
+__device__ long long g_tc_trace[16][24];
+#define GS_TR(k) do { if (blockIdx.x == 7 && it == 5 && lane == 0) g_tc_trace[warp][k] = clock64(); } while (0)
+#else
+#define GS_TR(k) do { } while (0)
+#endif
 
 // operands are stored as (hi, lo) = (rn_tf32(x), x - hi): see tc_common.cuh::tf32_rn
 
-// 16 values of the thread's row chunk -> TMEM A columns (hi = full fp32: the tensor core ignores the low 13 bits; lo = rest)
-__device__ __forceinline__ void chunk_to_tmem(uint32_t lane_addr, int c, const float (&v)[16]) {
+// 16 values of the thread's row chunk -> TMEM A columns (hi, lo)
+__device__ __forceinline__ void chunk_to_tmem(uint32_t a_addr /* lane | first column of the A buffer */, int c, const float (&v)[16]) {
     float h[16], l[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { h[i] = tf32_rn(v[i]); l[i] = v[i] - h[i]; }
-    tmem_st16(lane_addr + tcu::cAhi + 16 * c, h);
-    tmem_st16(lane_addr + tcu::cAlo + 16 * c, l);
+    tmem_st16(a_addr + 16 * c, h);
+    tmem_st16(a_addr + 64 + 16 * c, l);
 }
-// the chunk -> column s of a [64 rows][128 samples] K-major swizzled tile (rows 16c .. 16c+15), hi and lo copies.
+// the chunk -> column s of a 64-row region of the transposed tile (rows 16c .. 16c+15), hi and lo copies.
 // A warp writes 128 contiguous bytes per row: conflict-free.
-__device__ __forceinline__ void chunk_to_transposed(float* hi, float* lo, int base_s, const int (&xo)[8], int c, const float (&v)[16]) {
-    const int b = base_s + c * 512;
+__device__ __forceinline__ void chunk_to_transposed(float* hi, float* lo, int base_hi, int base_lo, const int (&xo)[8], int c, const float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int idx = b + i * 32 + xo[i & 7];
+        const int o = (16 * c + i) * 32 + xo[i & 7];
         const float h = tf32_rn(v[i]);
-        hi[idx] = h;
-        lo[idx] = v[i] - h;
+        hi[base_hi + o] = h;
+        lo[base_lo + o] = v[i] - h;
     }
 }
 
@@ -110,46 +139,61 @@ __device__ __forceinline__ void chunk_stats(const float (&z)[16], float& s, floa
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
     return ((uint64_t)(0x40004040u) << 32) | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | 0x10000u);
 }
+// byte offset of k-step kk (8 samples) inside a transposed tile whose 32-sample slabs are `slab` bytes apart
+__device__ __forceinline__ uint32_t kstep(int kk, uint32_t slab) { return (uint32_t)(kk >> 2) * slab + (uint32_t)(kk & 3) * 32u; }
 
 // 3xTF32 groups, each issued by ONE thread ------------------------------------------------------------------------------------
 // A from TMEM (M=128 rows = lanes), B K-major smem [64 rows][64 k] (lo copy 16 KB after hi)
-__device__ __forceinline__ void issue_ts_64x64(uint32_t tmem_base, uint32_t b_hi_addr, uint32_t acc_col) {
+__device__ __forceinline__ void issue_ts_64x64(uint32_t tmem_base, uint32_t a_col, uint32_t b_hi_addr, uint32_t acc_col) {
     const uint32_t idesc = make_idesc_tf32(128, 64, 0, 0);
     uint32_t accumulate = 0;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t acol = tmem_base + (pass == 1 ? tcu::cAlo : tcu::cAhi);
-        const uint64_t bd = desc_sw128(b_hi_addr + (pass == 2 ? 16384u : 0u));
+        const uint32_t acol = tmem_base + a_col + (pass == 1 ? 64u : 0u);
+        const uint32_t b0 = b_hi_addr + (pass == 2 ? 16384u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-            mma_tf32_ts(tmem_base + acc_col, acol + kk * 8, bd + (uint64_t)(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc, accumulate);
+            mma_tf32_ts(tmem_base + acc_col, acol + kk * 8, desc_sw128(b0 + kstep(kk, 8192u)), idesc, accumulate);
             accumulate = 1;
         }
     }
 }
-// A = [64 rows][128 samples] K-major smem (lo copy 32 KB after hi); B = [NB rows][128 samples] (lo copy at +b_lo_off)
-template <int NB>
-__device__ __forceinline__ void issue_ss_wgrad(uint32_t tmem_acc, uint32_t a_addr, uint32_t b_addr, uint32_t b_lo_off, uint32_t accumulate) {
-    const uint32_t idesc = make_idesc_tf32(64, NB, 0, 0);
+// dW2 | db2: A = P (dz2^T, 64 rows), B = S + ones rows (h1^T, 72 rows; the lo pass has no ones rows: N = 64)
+__device__ __forceinline__ void issue_dw2(uint32_t tmem_acc, uint32_t th, uint32_t tl, uint32_t accumulate) {
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
-        const uint64_t ad = desc_sw128(a_addr + (pass == 1 ? 32768u : 0u));
-        const uint64_t bd = desc_sw128(b_addr + (pass == 2 ? b_lo_off : 0u));
+        const uint32_t idesc = make_idesc_tf32(64, pass == 2 ? 64 : 72, 0, 0);
+        const uint32_t a0 = pass == 1 ? tl : th, as = pass == 1 ? tcu::kLoSlab : tcu::kHiSlab;
+        const uint32_t b0 = (pass == 2 ? tl : th) + 64u * 128u, bs = pass == 2 ? tcu::kLoSlab : tcu::kHiSlab;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            mma_tf32(tmem_acc, ad + (uint64_t)(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4),
-                     bd + (uint64_t)(((kk >> 2) * (NB * 128) + (kk & 3) * 32) >> 4), idesc, accumulate);
+            mma_tf32(tmem_acc, desc_sw128(a0 + kstep(kk, as)), desc_sw128(b0 + kstep(kk, bs)), idesc, accumulate);
+            accumulate = 1;
+        }
+    }
+}
+// tail: A = [P ; S] (128 rows), B = Y (16 rows; lo copy 8 KB after hi)
+__device__ __forceinline__ void issue_tail(uint32_t tmem_acc, uint32_t th, uint32_t tl, uint32_t y, uint32_t accumulate) {
+    const uint32_t idesc = make_idesc_tf32(128, 16, 0, 0);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a0 = pass == 1 ? tl : th, as = pass == 1 ? tcu::kLoSlab : tcu::kHiSlab;
+        const uint32_t b0 = y + (pass == 2 ? 8192u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            mma_tf32(tmem_acc, desc_sw128(a0 + kstep(kk, as)), desc_sw128(b0 + kstep(kk, 2048u)), idesc, accumulate);
             accumulate = 1;
         }
     }
 }
 
 // Move the wgrad accumulators from TMEM into this CTA's fp32 partial-gradient vector (global, L2-resident) and let the next
-// MMA group restart from zero.  The tensor core accumulates with truncation, so a TMEM chain is kept to kFlushTiles tiles
+// MMA groups restart from zero.  The tensor core accumulates with truncation, so a TMEM chain is kept to kFlushTiles tiles
 // (bias ~1e-5 relative, measured); across chains the sums are round-to-nearest fp32 adds in a fixed order (deterministic).
-// M=64 accumulators: row m lives in lane (m/16)*32 + m%16, i.e. lanes 0..15 of the warps of quadrant m/16.
+//   dW2|db2 (M=64): row m lives in lane (m/16)*32 + m%16, i.e. lanes 0..15 of the warps of quadrant m/16.
+//   tail (M=128):   lane = row; rows 0..63: cols 0..6 dW1[row][d], col 7 db1[row]; rows 64..127: cols 8+r dWh[r][row-64].
 constexpr int kFlushTiles = 8;
-__device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int chunk, int lane, int D, int A, int has_value,
+__device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int chunk, int lane, int row, int D, int A, int has_value,
                                             const ParamOffsets& po, float* __restrict__ out, bool first) {
     const int mrow = quad * 16 + (lane & 15);
     const bool owner = lane < 16;
@@ -165,8 +209,9 @@ __device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int ch
     float v[16];
     tmem_ld16(lane_addr + tcu::cW2 + 16 * chunk, v);
     float s16[16];
-    if (chunk < 2) tmem_ld16(lane_addr + (chunk == 0 ? tcu::cWH : tcu::cB2), s16);   // cols 256..271: dWh^T | dW1 ; 272..287: db2 in col 7
+    if (chunk < 2) tmem_ld16(lane_addr + (chunk == 0 ? tcu::cC : tcu::cW2 + 64), s16);   // chunk 0: tail block; chunk 1: db2 in col 0
     tmem_ld_wait();
+    auto put = [&](int64_t idx, float val) { out[idx] = first ? val : out[idx] + val; };
     if (owner) {
         if (vec) {
 #pragma unroll
@@ -180,16 +225,18 @@ __device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int ch
 #pragma unroll
             for (int i = 0; i < 16; ++i) d1[i] = first ? v[i] : d1[i] + v[i];
         }
-        auto put = [&](int64_t idx, float val) { out[idx] = first ? val : out[idx] + val; };
-        if (chunk == 0) {
+        if (chunk == 1) put(po.b2 + mrow, s16[0]);
+    }
+    if (chunk == 0) {
+        if (row < 64) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) if (r < A) put(po.wp + r * 64 + mrow, s16[r]);
-            if (has_value) put(po.wv + mrow, A == 2 ? s16[2] : s16[3]);
+            for (int d = 0; d < 7; ++d) if (d < D) put(po.w1 + row * D + d, s16[d]);
+            put(po.b1 + row, s16[7]);
+        } else {
+            const int k = row - 64;
 #pragma unroll
-            for (int d = 0; d < 7; ++d) if (d < D) put(po.w1 + mrow * D + d, s16[8 + d]);
-            put(po.b1 + mrow, s16[15]);
-        } else if (chunk == 1) {
-            put(po.b2 + mrow, s16[7]);
+            for (int r = 0; r < 3; ++r) if (r < A) put(po.wp + r * 64 + k, s16[8 + r]);
+            if (has_value) put(po.wv + k, A == 2 ? s16[10] : s16[11]);
         }
     }
 }
@@ -197,16 +244,13 @@ __device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int ch
 template <int ALGO, bool TRACK, bool D4, int ACT>
 __global__ void __launch_bounds__(tcu::kT, 1)
 update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom, const double* __restrict__ ret_mom,
-                 float* __restrict__ grad_partials, int64_t pstride, double* __restrict__ metric_partials, uint32_t* __restrict__ dead) {
+                 const uint32_t* __restrict__ offs /* time-major offset of every minibatch position */, float* __restrict__ grad_partials,
+                 int64_t pstride, double* __restrict__ metric_partials, uint32_t* __restrict__ dead) {
     extern __shared__ __align__(1024) unsigned char smraw[];
-    float* Qhi = reinterpret_cast<float*>(smraw + tcu::oQ);
-    float* Qlo = Qhi + 8192;
-    float* Rhi = reinterpret_cast<float*>(smraw + tcu::oR);
-    float* Rlo = Rhi + 8192;
-    float* GThi = reinterpret_cast<float*>(smraw + tcu::oGT);
-    float* GTlo = GThi + 1024;
-    float* XThi = reinterpret_cast<float*>(smraw + tcu::oXT);
-    float* XTlo = XThi + 1024;
+    float* TH = reinterpret_cast<float*>(smraw + tcu::oTH);
+    float* TL = reinterpret_cast<float*>(smraw + tcu::oTL);
+    float* Yhi = reinterpret_cast<float*>(smraw + tcu::oY);
+    float* Ylo = Yhi + 2048;
     float* w1s = reinterpret_cast<float*>(smraw + tcu::oW1);
     float* b1s = reinterpret_cast<float*>(smraw + tcu::oB1);
     float* b2s = reinterpret_cast<float*>(smraw + tcu::oB2);
@@ -215,22 +259,19 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + tcu::oBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smraw + tcu::oTmem);
     double* red = reinterpret_cast<double*>(smraw + tcu::oRed);
-    float4* outp = reinterpret_cast<float4*>(smraw + tcu::oOutP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127;              // sample row of the tile == TMEM lane
     const int chunk = tid >> 7;             // 16-column chunk of the row this thread owns
     const int quad = warp & 3;              // TMEM lane quadrant of the warp
-    const bool row_owner = chunk == 0;      // does the per-row scalar work (gather, loss)
+    const bool row_owner = chunk == 0;      // does the per-row scalar work (gather, metrics, x^T / g^T)
     const int A = m.A;
     const ParamOffsets po = param_offsets(m.D, 64, 64, m.A, m.has_value);
 
     // ---- one-time staging ------------------------------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, tcu::kTmemCols);
     if (tid == 0) {
-        mbar_init(&bars[tcu::BAR_FWD], 1); mbar_init(&bars[tcu::BAR_H], 1); mbar_init(&bars[tcu::BAR_D], 1);
-        mbar_init(&bars[tcu::BAR_W], 2);   // dW2 and db2 groups are issued by two different warps
-        mbar_init(&bars[tcu::BAR_1], 1);
+        mbar_init(&bars[tcu::BAR_FWD], 1); mbar_init(&bars[tcu::BAR_D], 1); mbar_init(&bars[tcu::BAR_W], 1); mbar_init(&bars[tcu::BAR_T], 1);
         fence_mbar_init();
     }
     {
@@ -252,26 +293,39 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             whs[i] = r < A ? __ldg(m.wp + r * 64 + k) : ((r == A && m.has_value) ? __ldg(m.wv + k) : 0.f);
         }
         if (tid < 4) bhs[tid] = tid < A ? __ldg(m.bp + tid) : ((tid == A && m.has_value) ? __ldg(m.bv) : 0.f);
-        for (int i = tid; i < 1024; i += tcu::kT) { GThi[i] = 0.f; GTlo[i] = 0.f; XThi[i] = 0.f; XTlo[i] = 0.f; }
+        // the transposed tile and Y start as zeros: the first tail group (heads of the first tile only) reads all of them
+        float4* z4 = reinterpret_cast<float4*>(smraw + tcu::oTH);
+        for (int i = tid; i < (tcu::oW2 - tcu::oTH) / 16; i += tcu::kT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 4096; i += tcu::kT) Yhi[i] = 0.f;
         if (tid < PM_N + 2) red[tid] = 0.0;
     }
     __syncthreads();
-    // transposed-store constants of this thread (sample column s = row)
+    // transposed-store constants of this thread (sample column s = row): element (feature f, sample s) of a region sits at
+    // base + f*32 + xo[f & 7] floats, base = slab(s) + (s & 3)
     const int chunk_s = (row & 31) >> 2;
     int xo[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) xo[c] = (chunk_s ^ c) << 2;
-    const int base64 = (row >> 5) * 2048 + (row & 3);   // [64 rows][128] tiles
-    const int base8 = (row >> 5) * 256 + (row & 3);     // [8 rows][128] tiles
-    if (row_owner) XThi[base8 + 7 * 32 + xo[7]] = 1.0f; // ones row: bias gradients fall out of the same MMAs
+    const int base_hi = (row >> 5) * (tcu::kHiSlab / 4) + (row & 3);
+    const int base_lo = (row >> 5) * (tcu::kLoSlab / 4) + (row & 3);
+    const int base_y = (row >> 5) * 512 + (row & 3);
+    if (row_owner) {
+        TH[base_hi + 128 * 32 + xo[0]] = 1.0f;          // ones row behind S: db2 is column 64 of the dW2 accumulator
+        Yhi[base_y + 7 * 32 + xo[7]] = 1.0f;            // ones row of x^T: db1 is column 7 of the tail accumulator
+    }
+    float* Phi = TH;                 // P: rows 0..63
+    float* Plo = TL;
+    float* Shi = TH + 64 * 32;       // S: rows 64..127
+    float* Slo = TL + 64 * 32;
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = uniform(*tmem_slot);
+    const uint32_t warp_u = uniform((uint32_t)warp);   // warp index the compiler knows to be uniform: single-UTCHMMA issue
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t sQ = smem_u32(Qhi), sR = smem_u32(Rhi), sW2 = smem_u32(smraw + tcu::oW2), sW2T = smem_u32(smraw + tcu::oW2T);
-    const uint32_t sGT = smem_u32(GThi), sXT = smem_u32(XThi);
+    const uint32_t sTH = smem_u32(TH), sTL = smem_u32(TL), sY = smem_u32(Yhi);
+    const uint32_t sW2 = smem_u32(smraw + tcu::oW2), sW2T = smem_u32(smraw + tcu::oW2T);
 
     float adv_mean = 0.f, adv_den = 1.f, ret_mean = 0.f, ret_den = 1.f;
     if (hp.normalize_adv) norm_consts(adv_mom, adv_mean, adv_den);
@@ -286,94 +340,186 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
 
     float* out = grad_partials + (size_t)blockIdx.x * pstride;    // this CTA's partial gradient vector (16 B aligned)
     const int64_t n_tiles = (b.n + tcu::kRows - 1) / tcu::kRows;
-    uint32_t it = 0;
-    // software-pipelined gather: row owners load the next tile's sample while the current tile is being processed
+    const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1: the launcher sizes the grid to the tiles
+    // software-pipelined gather (row owners): the sample of the tile after next is loaded while two tiles are in flight, and
+    // its translated offset (offs[], written by gather_offsets_kernel) one tile earlier still, so no load waits on another
     float nx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int n_a = 0;
     float n_lp = 0.f, n_v = 0.f, n_adv = 0.f, n_ret = 0.f;
-    auto prefetch = [&](int64_t t_next) {
+    uint32_t n_off = 0;
+    auto load_off = [&](int64_t t) -> uint32_t {
+        const int64_t p = t * tcu::kRows + row;
+        return (t < n_tiles && p < b.n) ? __ldg(offs + p) : 0u;
+    };
+    // The gather is issued in four small bursts spread over the iteration (stage 0..3): a single burst of all 7 scattered
+    // loads of 128 rows (~900 sectors in flight) backs up the SM's L1TEX queue and stalls every warp's shared-memory loads
+    // behind it for ~4000 cycles (measured with the clock64 trace); 128-256 sectors at a time do not.
+    int64_t pf_off = 0;
+    bool pf_ok = false;
+    auto prefetch_stage = [&](int stage, int64_t t_next) {
+        if (stage == 0) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) nx[d] = 0.f;
-        n_a = 0; n_lp = n_v = n_adv = n_ret = 0.f;
-        const int64_t p = t_next * tcu::kRows + row;
-        if (row_owner && t_next < n_tiles && p < b.n) {
-            const int64_t off = sample_offset(b, p);
-            const float* o = b.obs + off * b.D;
-            if (D4) {
-                if (b.D == 4) { const float4 v4 = __ldg(reinterpret_cast<const float4*>(o)); nx[0] = v4.x; nx[1] = v4.y; nx[2] = v4.z; nx[3] = v4.w; }
-                else { const float2 v2 = __ldg(reinterpret_cast<const float2*>(o)); nx[0] = v2.x; nx[1] = v2.y; }
-            } else {
+            for (int d = 0; d < 8; ++d) nx[d] = 0.f;
+            n_a = 0; n_lp = n_v = n_adv = n_ret = 0.f;
+            const int64_t p = t_next * tcu::kRows + row;
+            pf_ok = t_next < n_tiles && p < b.n;
+            pf_off = (int64_t)n_off;
+            if (pf_ok) {
+                const float* o = b.obs + pf_off * b.D;
+                if (D4) {
+                    if (b.D == 4) { const float4 v4 = __ldg(reinterpret_cast<const float4*>(o)); nx[0] = v4.x; nx[1] = v4.y; nx[2] = v4.z; nx[3] = v4.w; }
+                    else { const float2 v2 = __ldg(reinterpret_cast<const float2*>(o)); nx[0] = v2.x; nx[1] = v2.y; }
+                } else {
 #pragma unroll
-                for (int d = 0; d < 7; ++d) if (d < b.D) nx[d] = __ldg(o + d);
+                    for (int d = 0; d < 7; ++d) if (d < b.D) nx[d] = __ldg(o + d);
+                }
             }
-            n_a = __ldg(b.actions + off);
-            n_lp = __ldg(b.logp_old + off);
-            n_adv = __ldg(b.adv + off);
-            n_ret = __ldg(b.ret + off);
-            if (ALGO == ALGO_PPO) n_v = __ldg(b.values_old + off);
+            n_off = load_off(t_next + gridDim.x);
+        } else if (stage == 1) {
+            if (pf_ok) { n_a = __ldg(b.actions + pf_off); n_lp = __ldg(b.logp_old + pf_off); }
+        } else if (stage == 2) {
+            if (pf_ok) { n_adv = __ldg(b.adv + pf_off); n_ret = __ldg(b.ret + pf_off); }
+        } else {
+            if (ALGO == ALGO_PPO && pf_ok) n_v = __ldg(b.values_old + pf_off);
         }
     };
-    prefetch(blockIdx.x);
+    if (row_owner) {
+        n_off = load_off(blockIdx.x);
+#pragma unroll
+        for (int st = 0; st < 4; ++st) prefetch_stage(st, blockIdx.x);
+    }
+
+    float g[4] = {0.f, 0.f, 0.f, 0.f};      // d(loss)/d(head outputs) of the tile entering its backward phase
+    float xk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // its observation (layer 1 is recomputed in the backward phase)
+    int s_a = 0;                            // gathered sample scalars of the tile in its forward phase (every chunk thread)
+    float s_lp = 0.f, s_v = 0.f, s_adv = 0.f, s_ret = 0.f;
 #pragma unroll 1
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        const int64_t pos = tile * tcu::kRows + row;
-        const bool valid = pos < b.n;
-        // ---- this tile's sample data was prefetched during the previous tile (row owners) --------------------------------------
-        float x[8];
+    for (int it = -1; it < n_my; ++it) {
+        const bool has_cur = it >= 0, has_next = it + 1 < n_my;
+        const uint32_t cur = (uint32_t)it & 1u, nxt = cur ^ 1u;
+        const uint32_t ph = cur;                                    // parity of the current tile's BAR_D / BAR_W completions
+        const uint32_t a_cur = tcu::cA + 128u * cur, a_nxt = tcu::cA + 128u * nxt;
+        const uint32_t acc_cur = tcu::cAcc + 64u * cur, acc_nxt = tcu::cAcc + 64u * nxt;
+        const int64_t tile_u = blockIdx.x + (int64_t)(it + 1) * gridDim.x;
+        const bool valid_u = has_next && (tile_u * tcu::kRows + row < b.n);
+        const bool flush_now = it > 0 && (it % kFlushTiles) == 0;
+        const uint32_t acc_w = (has_cur && (it % kFlushTiles) != 0) ? 1u : 0u;      // dW2|db2 accumulator
+        const uint32_t acc_t = (it == -1 || flush_now) ? 0u : 1u;                   // tail accumulator
+        uint32_t relu_mask = 0;             // ACT == relu: act'(h1) of the chunk; tanh: d1[]
+        float d1[ACT == GS_ACT_RELU ? 1 : 16];
+        // ---- B1(t): dz2 -> TMEM A[cur] and P, h1^T -> S, x^T -> Y ---------------------------------------------------------------
+        GS_TR(0);
+        if (has_cur) {
+            float dz[16];
+            {
+                float z[16];
+                tmem_ld16(lane_addr + acc_cur + 16 * chunk, z);
+                tmem_ld_wait();
 #pragma unroll
-        for (int d = 0; d < 8; ++d) x[d] = nx[d];
-        const int a_s = n_a;
-        const float lp_old = n_lp, v_old = n_v, adv_s = n_adv, ret_s = n_ret;
-        prefetch(tile + gridDim.x);                 // global-load latency of the NEXT tile hides behind this tile's work
-        // previous tile's last MMAs (dW1: reads Q and x^T) must be done before Q / x^T / TMEM-A are rewritten
-        if (it > 0) {
-            mbar_wait(&bars[tcu::BAR_1], ph ^ 1);
+                for (int i = 0; i < 16; i += 4) {
+                    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 w = *reinterpret_cast<const float4*>(whs + r * 64 + 16 * chunk + i);
+                        d.x = fmaf(g[r], w.x, d.x); d.y = fmaf(g[r], w.y, d.y); d.z = fmaf(g[r], w.z, d.z); d.w = fmaf(g[r], w.w, d.w);
+                    }
+                    const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * chunk + i);
+                    dz[i] = d.x * act_bwd(act_fwd(z[i] + bb.x, ACT), ACT);
+                    dz[i + 1] = d.y * act_bwd(act_fwd(z[i + 1] + bb.y, ACT), ACT);
+                    dz[i + 2] = d.z * act_bwd(act_fwd(z[i + 2] + bb.z, ACT), ACT);
+                    dz[i + 3] = d.w * act_bwd(act_fwd(z[i + 3] + bb.w, ACT), ACT);
+                }
+            }
+            chunk_to_tmem(lane_addr + a_cur, chunk, dz);             // A[cur] is free: fwd(t) completed
+            GS_TR(16);
+            // the previous tail group reads P, S and Y: it must be done before they are rewritten
+            mbar_wait(&bars[tcu::BAR_T], ph);                        // completion index it (iteration -1 issued #0)
             fence_after_sync();
-            if (it % kFlushTiles == 0) flush_wgrad(lane_addr, quad, chunk, lane, m.D, A, m.has_value, po, out, it == kFlushTiles);
-        }
-        const uint32_t acc_flag = (it % kFlushTiles) != 0 ? 1u : 0u;
-        if (row_owner) {
+            if (flush_now) flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, it == kFlushTiles);
+            GS_TR(17);
+            chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
+            GS_TR(18);
+            float z[16];
+            layer1_chunk<D4>(w1s, b1s, xk, chunk, z);
 #pragma unroll
-            for (int d = 0; d < 7; ++d) {
-                const int idx = base8 + d * 32 + xo[d];
-                const float xh = tf32_rn(x[d]);
-                XThi[idx] = xh; XTlo[idx] = x[d] - xh;
+            for (int i = 0; i < 16; ++i) {
+                z[i] = act_fwd(z[i], ACT);
+                if (ACT == GS_ACT_RELU) relu_mask |= (z[i] > 0.f ? 1u : 0u) << i;
+                else d1[ACT == GS_ACT_RELU ? 0 : i] = 1.0f - z[i] * z[i];
+            }
+            GS_TR(19);
+            chunk_to_transposed(Shi, Slo, base_hi, base_lo, xo, chunk, z);
+            if (row_owner) {
+#pragma unroll
+                for (int d = 0; d < 7; ++d) {
+                    const int idx = base_y + d * 32 + xo[d];
+                    const float xh = tf32_rn(xk[d]);
+                    Yhi[idx] = xh; Ylo[idx] = xk[d] - xh;
+                }
             }
         }
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-        // ---- layer 1 chunk: h1 -> TMEM A (forward operand) and h1^T -> Q (wgrad operand) ----------------------------------------
-        if (!row_owner) {
+        // ---- owners: the next tile's gathered sample -> TMEM scratch (read by the row's other chunk threads) ----------------------
+        if (has_next && row_owner) {
+            float sx[16];
 #pragma unroll
-            for (int d = 0; d < 7; ++d) x[d] = XThi[base8 + d * 32 + xo[d]] + XTlo[base8 + d * 32 + xo[d]];
+            for (int d = 0; d < 8; ++d) sx[d] = nx[d];
+            sx[8] = __int_as_float(n_a); sx[9] = n_lp; sx[10] = n_v; sx[11] = n_adv; sx[12] = n_ret;
+            sx[13] = sx[14] = sx[15] = 0.f;
+            tmem_st16(lane_addr + tcu::cSX, sx);
         }
-        {
-            float z[16];
-            layer1_chunk<D4>(w1s, b1s, x, chunk, z);
-            if (TRACK && valid) chunk_stats(z, zs0, zq0, dead + 16 * chunk);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i], ACT);
-            chunk_to_tmem(lane_addr, chunk, z);
-            chunk_to_transposed(Qhi, Qlo, base64, xo, chunk, z);
-        }
+        GS_TR(1);
         tmem_st_wait();
         fence_proxy_async();
         fence_before_sync();
-        __syncthreads();
+        __syncthreads();                                                                                        // sync 1
         fence_after_sync();
-        if (tid == 0) { issue_ts_64x64(tmem, sW2, tcu::cAcc); mma_commit(&bars[tcu::BAR_FWD]); }
-        // ---- layer 2 epilogue: z2 chunk from TMEM, h2^T -> R (head-wgrad operand), partial head dot products ---------------------
-        mbar_wait(&bars[tcu::BAR_FWD], ph);
-        fence_after_sync();
-        {
+        GS_TR(2);
+        if (has_cur) {
+            if (warp_u == 0 && elect_one()) { issue_ts_64x64(tmem, a_cur, sW2T, acc_cur); mma_commit(&bars[tcu::BAR_D]); }      // dgrad
+            if (warp_u == 1 && elect_one()) { issue_dw2(tmem + tcu::cW2, sTH, sTL, acc_w); mma_commit(&bars[tcu::BAR_W]); }     // dW2 | db2
+        }
+        GS_TR(3);
+        // ---- F1(u): layer 1 -> h1 -> TMEM A[nxt] -------------------------------------------------------------------------------
+        if (has_next) {
+            float sx[16];
+            tmem_ld16(lane_addr + tcu::cSX, sx);
+            tmem_ld_wait();
+            s_a = __float_as_int(sx[8]); s_lp = sx[9]; s_v = sx[10]; s_adv = sx[11]; s_ret = sx[12];
+            GS_TR(20);
+            if (row_owner) prefetch_stage(0, tile_u + gridDim.x);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) xk[d] = sx[d];
             float z[16];
-            tmem_ld16(lane_addr + tcu::cAcc + 16 * chunk, z);
+            GS_TR(21);
+            layer1_chunk<D4>(w1s, b1s, xk, chunk, z);
+            GS_TR(22);
+            if (TRACK && valid_u) chunk_stats(z, zs0, zq0, dead + 16 * chunk);
+            GS_TR(23);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i], ACT);
+            chunk_to_tmem(lane_addr + a_nxt, chunk, z);              // A[nxt] is free: dgrad(t-1) completed
+            if (row_owner) prefetch_stage(1, tile_u + gridDim.x);
+        }
+        GS_TR(4);
+        tmem_st_wait();
+        fence_before_sync();
+        __syncthreads();                                                                                        // sync 2
+        fence_after_sync();
+        GS_TR(7);
+        if (has_next && warp_u == 2 && elect_one()) { issue_ts_64x64(tmem, a_nxt, sW2, acc_nxt); mma_commit(&bars[tcu::BAR_FWD]); }   // fwd(u)
+        GS_TR(8);
+        if (has_next && row_owner) prefetch_stage(2, tile_u + gridDim.x);
+        // ---- F2(u): z2 -> h2 -> this chunk's share of the head outputs -> TMEM scratch ------------------------------------------
+        if (has_next) {
+            mbar_wait(&bars[tcu::BAR_FWD], nxt);                     // completion index it+1
+            fence_after_sync();
+            GS_TR(9);
+            float z[16];
+            tmem_ld16(lane_addr + acc_nxt + 16 * chunk, z);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] += b2s[16 * chunk + i];
-            if (TRACK && valid) chunk_stats(z, zs1, zq1, dead + 64 + 16 * chunk);
+            if (TRACK && valid_u) chunk_stats(z, zs1, zq1, dead + 64 + 16 * chunk);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i], ACT);
             float o4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -386,97 +532,84 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                     o4[r] = fmaf(z[i + 2], w.z, o4[r]); o4[r] = fmaf(z[i + 3], w.w, o4[r]);
                 }
             }
-            outp[chunk * 128 + row] = make_float4(o4[0], o4[1], o4[2], o4[3]);
-            chunk_to_transposed(Rhi, Rlo, base64, xo, chunk, z);   // R is free: BAR_1 of the previous tile implies its BAR_W
+            tmem_st4(lane_addr + tcu::cOP + 4 * chunk, o4);
         }
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-        // ---- loss (row owners) ---------------------------------------------------------------------------------------------
-        if (row_owner) {
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                const float4 p0 = outp[row], p1 = outp[128 + row], p2 = outp[256 + row], p3 = outp[384 + row];
-                float outv[4];
-                outv[0] = bhs[0] + ((p0.x + p1.x) + (p2.x + p3.x)); outv[1] = bhs[1] + ((p0.y + p1.y) + (p2.y + p3.y));
-                outv[2] = bhs[2] + ((p0.z + p1.z) + (p2.z + p3.z)); outv[3] = bhs[3] + ((p0.w + p1.w) + (p2.w + p3.w));
-                sample_loss<ALGO>(outv, A, a_s, lp_old, v_old, adv_s, ret_s, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) gsum[r] += g[r];
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int idx = base8 + r * 32 + xo[r];
-                const float gh = tf32_rn(g[r]);
-                GThi[idx] = gh; GTlo[idx] = g[r] - gh;
-            }
-        }
-        fence_proxy_async();
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-        if (tid == 32) { issue_ss_wgrad<8>(tmem + tcu::cWH, sR, sGT, 4096u, acc_flag); mma_commit(&bars[tcu::BAR_H]); }
-        // ---- dz2 chunk = (g . Wh) * act'(h2): h2 re-derived from the z2 accumulator still in TMEM --------------------------------
-        float dz[16];
-        {
-            float g[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) g[r] = GThi[base8 + r * 32 + xo[r]] + GTlo[base8 + r * 32 + xo[r]];
-            tmem_ld16(lane_addr + tcu::cAcc + 16 * chunk, dz);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float4 w = *reinterpret_cast<const float4*>(whs + r * 64 + 16 * chunk + i);
-                    d.x = fmaf(g[r], w.x, d.x); d.y = fmaf(g[r], w.y, d.y); d.z = fmaf(g[r], w.z, d.z); d.w = fmaf(g[r], w.w, d.w);
-                }
-                const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * chunk + i);
-                dz[i] = d.x * act_bwd(act_fwd(dz[i] + bb.x, ACT), ACT);
-                dz[i + 1] = d.y * act_bwd(act_fwd(dz[i + 1] + bb.y, ACT), ACT);
-                dz[i + 2] = d.z * act_bwd(act_fwd(dz[i + 2] + bb.z, ACT), ACT);
-                dz[i + 3] = d.w * act_bwd(act_fwd(dz[i + 3] + bb.w, ACT), ACT);
-            }
-        }
-        chunk_to_tmem(lane_addr, chunk, dz);            // TMEM A is free (forward MMAs completed)
-        mbar_wait(&bars[tcu::BAR_H], ph);               // head wgrad has consumed h2^T: R may be overwritten
-        fence_after_sync();
-        chunk_to_transposed(Rhi, Rlo, base64, xo, chunk, dz);
+        GS_TR(10);
         tmem_st_wait();
-        fence_proxy_async();
         fence_before_sync();
-        __syncthreads();
+        __syncthreads();                                                                                        // sync 3
         fence_after_sync();
-        if (tid == 0) { issue_ts_64x64(tmem, sW2T, tcu::cAcc); mma_commit(&bars[tcu::BAR_D]); }                               // dgrad
-        if (tid == 32) { issue_ss_wgrad<64>(tmem + tcu::cW2, sR, sQ, 32768u, acc_flag); mma_commit(&bars[tcu::BAR_W]); }      // dW2
-        if (tid == 64) { issue_ss_wgrad<8>(tmem + tcu::cB2, sR, sXT, 4096u, acc_flag); mma_commit(&bars[tcu::BAR_W]); }       // db2
-        // ---- dz1 chunk = dh1 * act'(h1) -> dz1^T -> Q -------------------------------------------------------------------------------
-        {
-            float h1[16];
-            layer1_chunk<D4>(w1s, b1s, x, chunk, h1);    // overlaps the dgrad MMAs
+        GS_TR(11);
+        // ---- F3(u): loss and d(loss)/d(heads), redundantly by the four chunk threads of the row (metrics: the owner) -------------
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[r] = 0.f;
+        if (has_next) {
+            float op[16];
+            tmem_ld16(lane_addr + tcu::cOP, op);
+            tmem_ld_wait();
+            if (valid_u) {
+                float outv[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) outv[r] = bhs[r] + ((op[r] + op[4 + r]) + (op[8 + r] + op[12 + r]));
+                if (row_owner) {
+                    sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) gsum[r] += g[r];
+                } else {
+                    float pm_unused[PM_N];
+#pragma unroll
+                    for (int i = 0; i < PM_N; ++i) pm_unused[i] = 0.f;
+                    sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm_unused);
+                }
+            }
+        }
+        if (row_owner) {                                             // Y is free: every thread waited for the previous tail in B1
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {                            // zeros when there is no next tile: the tail's heads block adds 0
+                const int idx = base_y + (8 + r) * 32 + xo[r];
+                const float gh = tf32_rn(g[r]);
+                Yhi[idx] = gh; Ylo[idx] = g[r] - gh;
+            }
+            if (has_next) prefetch_stage(3, tile_u + gridDim.x);
+        }
+        GS_TR(12);
+        // ---- dz1(t) = dh1 * act'(h1) -> dz1^T -> P ; h2^T(u) -> S -----------------------------------------------------------------
+        if (has_cur) {
+            float dz[16];
             mbar_wait(&bars[tcu::BAR_D], ph);
             fence_after_sync();
-            tmem_ld16(lane_addr + tcu::cAcc + 16 * chunk, dz);
+            tmem_ld16(lane_addr + acc_cur + 16 * chunk, dz);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dz[i] *= act_bwd(act_fwd(h1[i], ACT), ACT);
+            for (int i = 0; i < 16; ++i) {
+                if (ACT == GS_ACT_RELU) dz[i] = ((relu_mask >> i) & 1u) ? dz[i] : 0.f;
+                else dz[i] *= d1[ACT == GS_ACT_RELU ? 0 : i];
+            }
+            GS_TR(13);
+            mbar_wait(&bars[tcu::BAR_W], ph);                        // dW2 has consumed dz2^T and h1^T: P and S may be overwritten
+            fence_after_sync();
+            GS_TR(14);
+            chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
         }
-        mbar_wait(&bars[tcu::BAR_W], ph);               // wgrad has consumed h1^T: Q may be overwritten
-        fence_after_sync();
-        chunk_to_transposed(Qhi, Qlo, base64, xo, chunk, dz);
+        if (has_next) {
+            float z[16];
+            tmem_ld16(lane_addr + acc_nxt + 16 * chunk, z);          // z2(u) is still in its accumulator: h2 is re-derived
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i] + b2s[16 * chunk + i], ACT);
+            chunk_to_transposed(Shi, Slo, base_hi, base_lo, xo, chunk, z);
+        }
+        GS_TR(15);
         fence_proxy_async();
         fence_before_sync();
-        __syncthreads();
+        __syncthreads();                                                                                        // sync 4
         fence_after_sync();
-        if (tid == 96) { issue_ss_wgrad<8>(tmem + tcu::cW1, sQ, sXT, 4096u, acc_flag); mma_commit(&bars[tcu::BAR_1]); }
+        if (warp_u == 3 && elect_one()) { issue_tail(tmem + tcu::cC, sTH, sTL, sY, acc_t); mma_commit(&bars[tcu::BAR_T]); }     // dW1 | db1 | dWh
     }
-    // ---- drain: wait for the last MMAs and flush what the TMEM accumulators still hold -------------------------------------
-    if (it > 0) {
-        mbar_wait(&bars[tcu::BAR_1], (it - 1) & 1);
-        fence_after_sync();
-        flush_wgrad(lane_addr, quad, chunk, lane, m.D, A, m.has_value, po, out, it <= kFlushTiles);
-    }
+    // ---- drain: wait for the last tail group and flush what the TMEM accumulators still hold --------------------------------
+    mbar_wait(&bars[tcu::BAR_T], (uint32_t)n_my & 1u);               // completion index n_my
+    fence_after_sync();
+    flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, n_my <= kFlushTiles);
     // ---- block reductions through shared-memory atomics: head biases (4 floats) and the metric partials (PM_N doubles) ------
     float* fr = reinterpret_cast<float*>(red + PM_N);
     if (TRACK) { pm[PM_Z0] = zs0; pm[PM_Z0SQ] = zq0; pm[PM_Z1] = zs1; pm[PM_Z1SQ] = zq1; }
@@ -507,9 +640,9 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
 // ---- host launcher (called from update_kernels.cu::launch_update for the 64x64 network) ----------------------------------------
 template <int ALGO>
 int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
-                     float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid, cudaStream_t st) {
+                     const uint32_t* offs, float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid, cudaStream_t st) {
     const bool d4 = md.D <= 4 && (md.D == 4 || md.D == 2);
-    using KernelFn = void (*)(MlpDev, BatchDev, HpDev, const double*, const double*, float*, int64_t, double*, uint32_t*);
+    using KernelFn = void (*)(MlpDev, BatchDev, HpDev, const double*, const double*, const uint32_t*, float*, int64_t, double*, uint32_t*);
     auto pick_act = [&](auto act_tag) -> KernelFn {
         constexpr int ACT = decltype(act_tag)::value;
         if (track) return d4 ? update_tc_kernel<ALGO, true, true, ACT> : update_tc_kernel<ALGO, true, false, ACT>;
@@ -521,11 +654,17 @@ int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool 
     };
     auto kern = pick();
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcu::kSmemBytes));
-    kern<<<grid, tcu::kT, tcu::kSmemBytes, st>>>(md, b, hp, adv_mom, ret_mom, grad_partials, pstride, metric_partials, dead);
+    kern<<<grid, tcu::kT, tcu::kSmemBytes, st>>>(md, b, hp, adv_mom, ret_mom, offs, grad_partials, pstride, metric_partials, dead);
     GS_LAUNCH_CHECK();
     return 0;
 }
-template int launch_update_tc<ALGO_PPO>(const MlpDev&, const BatchDev&, const HpDev&, bool, const double*, const double*, float*, int64_t, double*, uint32_t*, int, cudaStream_t);
-template int launch_update_tc<ALGO_REINFORCE>(const MlpDev&, const BatchDev&, const HpDev&, bool, const double*, const double*, float*, int64_t, double*, uint32_t*, int, cudaStream_t);
+template int launch_update_tc<ALGO_PPO>(const MlpDev&, const BatchDev&, const HpDev&, bool, const double*, const double*, const uint32_t*, float*, int64_t, double*, uint32_t*, int, cudaStream_t);
+template int launch_update_tc<ALGO_REINFORCE>(const MlpDev&, const BatchDev&, const HpDev&, bool, const double*, const double*, const uint32_t*, float*, int64_t, double*, uint32_t*, int, cudaStream_t);
 
 }  // namespace gs
+
+#ifdef GS_TC_TRACE
+extern "C" int gs_debug_tc_trace(long long* host_out /* [16][24] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_tc_trace, sizeof(long long) * 384);
+}
+#endif

@@ -245,7 +245,9 @@ int gs_batch_moments(const gs_batch_t* batch, const float* field /* (T,N) */, do
  * partials: workspace of gs_update_workspace_bytes(); grads_flat (P,) receives dLoss/dtheta (deterministic
  * two-stage reduction); metrics (double[GS_N_METRICS]) receives the finalised scalars of the metric enum.
  * adv_moments: device double[3] from gs_batch_moments when hp.normalize_adv == 1, else nullable. */
-int64_t gs_update_workspace_bytes(const gs_mlp_t* mlp, int device);
+/* Bytes of device scratch gs_ppo_step / gs_reinforce_step need for minibatches of up to max_batch samples (per-CTA partial
+ * gradients and metrics + 4 bytes per sample for the translated sample offsets). */
+int64_t gs_update_workspace_bytes(const gs_mlp_t* mlp, int device, int64_t max_batch);
 /* Kernel selection for gs_ppo_step / gs_reinforce_step: 0 (default) = tcgen05 tensor-core kernel where one exists (64x64
  * MLP: 3xTF32, fp32 TMEM accumulators), 1 = fp32 FMA-pipe kernel everywhere.  Env GS_UPDATE_IMPL=simt|tc sets the default. */
 int gs_set_update_impl(int impl);

@@ -200,7 +200,7 @@ def flat_to_time_major(x_flat, T, Nn):
 def update_step(algo, p_dev, batch, hp, *, activation="relu", max_norm=None):
     m = N.mlp_struct_from_params(p_dev, activation)
     P = N.lib().gs_mlp_param_count(C.byref(m))
-    wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0)
+    wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0, int(batch.n))
     assert P > 0 and wsb > 0, N.lib().gs_last_error()
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     grads = torch.full((P,), float("nan"), dtype=torch.float32, device=DEV)

@@ -27,6 +27,45 @@ def _assert_grads_close(g, ref, tol=1e-4):
     np.testing.assert_allclose(g, ref, rtol=tol, atol=tol * scale)
 
 
+def _away_from_kinks(p, obs, activation, gen, margin=2e-5, scale=1.0):
+    """Resample the observations whose hidden pre-activations land within `margin` of a ReLU kink.
+
+    A gradient of these synthetic batches is a sum of ~n cancelling terms of size 1/n, so ONE sample whose ReLU unit falls
+    on the other side of zero (|z| below the arithmetic noise of a summation order: ~1e-7 for fp32 FMA chains, ~3e-7 for the
+    3xTF32 tensor-core path) moves an entry by ~5e-4 of the gradient scale — a discontinuity of the loss, not an arithmetic
+    error.  Parity of the arithmetic is measured on batches without such samples (fp64 check, chunked)."""
+    if activation != "relu":
+        return obs
+    flat = obs.reshape(-1, obs.shape[-1])
+    w = {k: v.double() for k, v in p.items()}
+    for _ in range(50):
+        bad = torch.zeros(flat.shape[0], dtype=torch.bool)
+        for lo in range(0, flat.shape[0], 1 << 18):
+            x = flat[lo:lo + (1 << 18)].double()
+            z1 = x @ w["w1"].T + w["b1"]
+            b = z1.abs().lt(margin).any(-1)
+            if "w2" in w:
+                z2 = torch.relu(z1) @ w["w2"].T + w["b2"]
+                b |= z2.abs().lt(margin).any(-1)
+            bad[lo:lo + (1 << 18)] = b
+        if not bad.any():
+            return obs
+        flat[bad] = torch.randn(int(bad.sum()), flat.shape[1], generator=gen) * scale
+    raise AssertionError("could not move the batch away from the ReLU kinks")
+
+
+def _noise_away_from(noise, edges, gen, std, margin=1e-4):
+    """Resample noise entries within `margin` of a clipping edge (ratio = exp(-noise) vs 1 +- clip; |v - v_old| vs clip_vf)."""
+    for _ in range(50):
+        bad = torch.zeros_like(noise, dtype=torch.bool)
+        for e in edges:
+            bad |= (noise - e).abs() < margin
+        if not bad.any():
+            return noise
+        noise[bad] = std * torch.randn(int(bad.sum()), generator=gen)
+    raise AssertionError("could not move the noise away from the clipping edges")
+
+
 def _ppo_hp(N, clip=0.2, clip_vf=0.2, vf=0.5, ent=0.01, norm=True, track=True):
     hp = N.GsPpoHparams()
     hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef = clip, clip_vf, vf, ent
@@ -122,13 +161,16 @@ def test_ppo_step_full_size_minibatch_vs_oracle():
     T, Nn, D, A = 128, 65536, 4, 2
     g = torch.Generator().manual_seed(0)
     p = P.random_params(D, (64, 64), A, seed=1)
-    obs = torch.randn(T, Nn, D, generator=g) * 0.5
+    import math
+    obs = _away_from_kinks(p, torch.randn(T, Nn, D, generator=g) * 0.5, "relu", g, scale=0.5)
     actions = torch.randint(0, A, (T, Nn), generator=g)
     with torch.no_grad():
         logits, v = P.forward(p, obs.reshape(-1, D))
         lp_all = logits - logits.logsumexp(-1, keepdim=True)
-    old_logp = (lp_all.gather(-1, actions.reshape(-1, 1)).squeeze(-1) + 0.1 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
-    values_old = (v + 0.3 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    n_lp = _noise_away_from(0.1 * torch.randn(T * Nn, generator=g), [-math.log(1.2), -math.log(0.8)], g, 0.1)
+    n_v = _noise_away_from(0.3 * torch.randn(T * Nn, generator=g), [-0.2, 0.2], g, 0.3)
+    old_logp = (lp_all.gather(-1, actions.reshape(-1, 1)).squeeze(-1) + n_lp).reshape(T, Nn)
+    values_old = (v + n_v).reshape(T, Nn)
     adv = torch.randn(T, Nn, generator=g)
     ret = values_old + adv
     total, B = T * Nn, 1 << 20
@@ -149,10 +191,8 @@ def test_ppo_step_full_size_minibatch_vs_oracle():
     loss, flat, om = P.loss_and_grads(P.ppo_loss, p, sel(obs), sel(actions), sel(old_logp), sel(values_old), sel(adv), sel(ret),
                                       clip_range=0.2, clip_range_vf=0.2, vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
     ref = flat.numpy()
-    # 1M-sample fp32 sums in a different order than torch's; the default (tensor-core) kernel also sees ReLU units flip at
-    # |z2| < 1e-6 (see test_tensor_core_and_simt_update_kernels_agree), so the element-wise bar is 1e-3 of the gradient scale
-    # and the 1e-4 parity bar is held on the whole gradient vector.
-    _assert_grads_close(g_raw, ref, tol=1e-3)
+    # 1M-sample fp32 sums in a different order than torch's (the batch holds no sample on a ReLU / clipping kink)
+    _assert_grads_close(g_raw, ref, tol=2e-4)
     assert np.linalg.norm(g_raw - ref) <= 1e-4 * np.linalg.norm(ref)
     np.testing.assert_allclose(m["opt/loss/total"], float(loss), rtol=1e-4)
     for k in PPO_METRICS:
@@ -249,13 +289,14 @@ def test_tensor_core_and_simt_update_kernels_agree(algo, n, D, A, activation):
 
     g = torch.Generator().manual_seed(n + D)
     p = P.random_params(D, (64, 64), A, seed=n, has_value=True)
-    obs = torch.randn(1, n, D, generator=g)
+    import math
+    obs = _away_from_kinks(p, torch.randn(1, n, D, generator=g), activation, g)
     actions = torch.randint(0, A, (1, n), generator=g)
     with torch.no_grad():
         logits, v = P.forward(p, obs.reshape(-1, D), activation)
         lp = (logits - logits.logsumexp(-1, keepdim=True)).gather(-1, actions.reshape(-1, 1)).squeeze(-1)
-    old_logp = (lp + 0.2 * torch.randn(n, generator=g)).reshape(1, n)
-    values_old = (v + 0.3 * torch.randn(n, generator=g)).reshape(1, n)
+    old_logp = (lp + _noise_away_from(0.2 * torch.randn(n, generator=g), [-math.log(1.15), -math.log(0.85)], g, 0.2)).reshape(1, n)
+    values_old = (v + _noise_away_from(0.3 * torch.randn(n, generator=g), [-0.25, 0.25], g, 0.3)).reshape(1, n)
     adv = torch.randn(1, n, generator=g) * 2 + 0.3
     ret = values_old + adv
     batch, keep = E.make_batch(1, n, E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret))
@@ -279,17 +320,14 @@ def test_tensor_core_and_simt_update_kernels_agree(algo, n, D, A, activation):
     scale = np.abs(ref).max()
     for impl in (0, 1):
         g_raw, g_clip, m = out[impl]
-        # The tensor-core kernel's z2 carries ~3e-7 absolute 3xTF32 error, so a few of the n*64 ReLU units whose pre-activation
-        # lies within 1e-6 of the kink switch sides (14 of 2.56M here at n=40000); each flip moves one row of dW2 by ~1e-4 of
-        # the gradient scale.  Element-wise bar 1e-3 of scale for that kernel, and the 1e-4 bar on the whole gradient (L2).
-        np.testing.assert_allclose(g_raw, ref, rtol=1e-4, atol=(1e-3 if impl == 0 else 1e-4) * scale, err_msg=f"impl {impl}")
+        np.testing.assert_allclose(g_raw, ref, rtol=1e-4, atol=1e-4 * scale, err_msg=f"impl {impl}")
         assert np.linalg.norm(g_raw - ref) <= 1e-4 * np.linalg.norm(ref), f"impl {impl}"
         np.testing.assert_allclose(m["opt/loss/total"], float(loss), rtol=1e-4, atol=1e-6)
         acts = om["_activations"]
         for name in acts:
             for stat in ("mean", "std"):
                 np.testing.assert_allclose(m[f"opt/activations/{name}/{stat}"], acts[name][stat], rtol=1e-4, atol=1e-6, err_msg=f"impl {impl} {name}/{stat}")
-    np.testing.assert_allclose(out[0][0], out[1][0], rtol=2e-5, atol=(1e-3 if n > 5000 else 2e-5) * scale)
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=2e-5, atol=2e-5 * scale)
     assert np.linalg.norm(out[0][0] - out[1][0]) <= 1e-4 * np.linalg.norm(out[1][0])
     for k in ("opt/loss/total", "opt/ppo/kl", "opt/ppo/approx_kl", "opt/policy/entropy", "opt/grads/norm/all"):
         np.testing.assert_allclose(out[0][2][k], out[1][2][k], rtol=1e-5, atol=1e-7, err_msg=k)
