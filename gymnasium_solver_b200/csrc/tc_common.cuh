@@ -103,6 +103,9 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef GS_MBAR_HINT_NS
+#define GS_MBAR_HINT_NS 0x400
+#endif
 // ---- mbarrier -----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -111,16 +114,17 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: traps instead of hanging the GPU if the phase never completes (a kernel bug, never a legal state)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t done;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n\t"   // suspend-time hint: sleep, do not spin
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint (ns): sleep, do not spin
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"((uint32_t)GS_MBAR_HINT_NS)
             : "memory");
         if (done) return;
     }
@@ -153,6 +157,18 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- cp.async (global -> shared without a register round trip) ---------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // tf32 split: hi keeps the top 19 bits (what the tensor core reads), lo = x - hi (exact in fp32)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {

@@ -68,9 +68,11 @@ __device__ __forceinline__ void sample_loss(const float (&out)[kNH], int A, int 
         if (k < A) { p[k] = expf(lp[k]); H -= p[k] * lp[k]; }
     const float logp = a_s == 0 ? lp[0] : (a_s == 1 ? lp[1] : lp[2]);
     float dlogp;
+    float ratio_ppo = 0.f;
     if (ALGO == ALGO_PPO) {
         const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
         const float ratio = expf(logp - lp_old);
+        ratio_ppo = ratio;
         const float rc = fminf(fmaxf(ratio, hp.clip_lo), hp.clip_hi);
         const float s1 = adv_n * ratio, s2 = adv_n * rc;
         const bool inrange = (ratio >= hp.clip_lo) && (ratio <= hp.clip_hi);
@@ -110,8 +112,9 @@ __device__ __forceinline__ void sample_loss(const float (&out)[kNH], int A, int 
         if (k < A) g[k] = dlogp * ((k == a_s ? 1.f : 0.f) - p[k]) + ec_b * p[k] * (lp[k] + H);
     pm[PM_ENT] += H;
     pm[PM_KL] += lp_old - logp;
-    const float dcl = fminf(fmaxf(logp - lp_old, -20.f), 20.f);   // utils/torch.py:115-118
-    const float r2 = expf(dcl);
+    const float dlp = logp - lp_old;
+    const float dcl = fminf(fmaxf(dlp, -20.f), 20.f);             // utils/torch.py:115-118
+    const float r2 = (ALGO == ALGO_PPO && dcl == dlp) ? ratio_ppo : expf(dcl);   // same argument as the surrogate's ratio: same bits
     pm[PM_AKL] += (r2 - 1.f) - logf(r2);
     pm[PM_COUNT] += 1.f;
 }

@@ -18,24 +18,28 @@
 // 64-row halves of ONE 128-row tile (+ 8 rows holding the ones row behind S), so the same bytes serve as M=64 / N=72
 // operands of dW2 and as the M=128 operand of the tail group.
 //
-// Schedule: 1 CTA of 512 threads per SM (thread = sample row x 16-column chunk), 216 KB shared memory, all 512 TMEM columns.
-// The loop is software-pipelined over tiles: iteration `it` runs the BACKWARD phase of tile t and the FORWARD phase of the
-// next tile u in one instruction stream, so every MMA group has independent SIMT work behind it:
+// Schedule: 1 CTA per SM = 16 compute warps (thread = sample row x 16-column chunk) + 1 MMA-issuing warp, 227 KB shared
+// memory, all 512 TMEM columns.  tcgen05.mma issue blocks the issuing warp for as long as the tensor pipe is busy (the
+// queue is shallow: measured with the clock64 trace), so it gets a warp of its own; the compute warps synchronise among
+// themselves on a named barrier and hand operands over through mbarriers.  The loop is software-pipelined over tiles:
+// iteration `it` runs the BACKWARD phase of tile t and the FORWARD phase of the next tile u in one instruction stream, so
+// every MMA group has independent SIMT work behind it:
 //
-//   B1(t)  z2 -> dz2 -> TMEM A[cur] ; wait tail(t-1) ; dz2^T -> P, h1^T -> S, x^T(t) -> Y    | owners: sample(u) -> TMEM scratch
-//   ---- sync 1 ----   issue dgrad(t) [A[cur] -> acc[cur]], dW2(t) [P,S]
+//   B1(t)  z2 -> dz2 -> TMEM A[cur], layer 1 again -> h1 ; wait tail(t-1) ; dz2^T -> P, h1^T -> S, x^T(t) -> Y
+//          owners: sample(u) -> TMEM scratch
+//   ---- sync 1 ---- ready[0]:  MMA warps issue dgrad(t) [A[cur] -> acc[cur]] and dW2(t) [P,S]
 //   F1(u)  layer 1 -> h1(u) -> TMEM A[nxt]
-//   ---- sync 2 ----   issue fwd(u) [A[nxt] -> acc[nxt]]
+//   ---- sync 2 ---- ready[1]:  MMA warp issues fwd(u) [A[nxt] -> acc[nxt]]
+//          wait dgrad(t), dW2(t) ; dz1^T(t) -> P
 //   F2(u)  wait fwd(u); z2 -> h2 -> partial head outputs -> TMEM scratch
 //   ---- sync 3 ----
-//   F3(u)  loss, d(loss)/d(heads) -> g (every chunk thread of the row; metrics by the row owner), g^T(u) -> Y
-//          wait dgrad(t), dW2(t) ; dz1^T(t) -> P, h2^T(u) -> S
-//   ---- sync 4 ----   issue tail(t,u) [P;S, Y]
+//   F3(u)  loss, d(loss)/d(heads) -> g (every chunk thread of the row; metrics by the chunk-1 thread), g^T(u) -> Y, h2^T(u) -> S
+//   ---- sync 4 ---- ready[2]:  MMA warp issues tail(t,u) [P;S, Y]
 //
 // TMEM A operands and the z2 / dh1 accumulator are double-buffered (cur/nxt); the transposed operand tile is single
 // (shared memory is the limit).  Per-row exchanges between the four chunk threads of a row (head partial sums, gathered
-// sample) go through spare TMEM columns: all four warps of a quadrant address the same lanes.  Each MMA group is issued by
-// one warp (elect.sync), one accumulator each, so every accumulation order is fixed (deterministic).
+// sample) go through spare TMEM columns: all four warps of a quadrant address the same lanes.  All MMAs are issued by one
+// thread in a fixed order, so every accumulation order is fixed (deterministic).
 #include <type_traits>
 
 #include "mlp_tile.cuh"
@@ -48,7 +52,8 @@ using namespace tc;
 
 namespace tcu {
 constexpr int kRows = 128;              // samples per tile == TMEM lanes
-constexpr int kT = 512;                 // threads: thread = (row, 16-column chunk); warp w -> rows 32*(w&3).., chunk w>>2
+constexpr int kCompute = 512;           // compute threads: thread = (row, 16-column chunk); warp w -> rows 32*(w&3).., chunk w>>2
+constexpr int kT = kCompute + 64;       // + two MMA-issuing warps (16: dgrad, fwd; 17: dW2, tail)
 // shared memory map (bytes).  Transposed operand tile: 4 slabs (32 samples each) x rows x 128 B.
 constexpr int kHiRows = 136;            // P rows 0..63, S rows 64..127, ones row 128 (+7 zero rows: N is a multiple of 8)
 constexpr int kHiSlab = kHiRows * 128;  // 17408 B
@@ -64,21 +69,27 @@ constexpr int oB1 = oW1 + 2048;
 constexpr int oB2 = oB1 + 256;
 constexpr int oWH = oB2 + 256;          // [4][64]
 constexpr int oBH = oWH + 1024;         // [4]
-constexpr int oBar = oBH + 16;          // 4 mbarriers
+constexpr int oBar = oBH + 16;          // 7 mbarriers
 constexpr int oTmem = oBar + 64;
-constexpr int oRed = oTmem + 16;        // PM_N doubles + 4 floats (block reductions through shared atomics)
-constexpr int kSmemBytes = oRed + 256;
+constexpr int oRed = oTmem + 16;        // PM_N doubles + 16 floats (block reductions)
+constexpr int oStage = oRed + 256;      // gather staging [128 rows][16] fp32 (cp.async destination)
+constexpr int kSmemBytes = oStage + 128 * 64;
 static_assert(oTL % 1024 == 0 && oW2 % 1024 == 0 && oY % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM columns: A[b] = 128*b (hi +0, lo +64); acc[b] = 256 + 64*b; dW2|db2 (72 used of 80); tail accumulator; per-row scratch
-constexpr uint32_t cA = 0, cAcc = 256, cW2 = 384, cC = 464, cOP = 480, cSX = 496, kTmemCols = 512;
-enum { BAR_FWD = 0, BAR_D, BAR_W, BAR_T };
+constexpr uint32_t cA = 0, cAcc = 256, cW2 = 384, cC = 464, cOP = 480, kTmemCols = 512;
+enum { BAR_FWD = 0, BAR_D, BAR_W, BAR_T, RDY_0, RDY_1, RDY_2 };   // MMA-complete barriers; operands-ready barriers
+// barrier among the 512 compute threads only (the MMA warp never joins it)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 }  // namespace tcu
 
 // Development aid (build with GS_NVCC_EXTRA=-DGS_TC_TRACE): per-warp clock64() stamps of one pipeline iteration of one CTA,
 // read back with gs_debug_tc_trace().  Not part of the ABI; absent from normal builds.
 #ifdef GS_TC_TRACE
-__device__ long long g_tc_trace[16][24];
+__device__ long long g_tc_trace[18][24];
 #define GS_TR(k) do { if (blockIdx.x == 7 && it == 5 && lane == 0) g_tc_trace[warp][k] = clock64(); } while (0)
 #else
 #define GS_TR(k) do { } while (0)
@@ -124,14 +135,21 @@ __device__ __forceinline__ void layer1_chunk(const float* w1s, const float* b1s,
 }
 
 // activation statistics of one chunk (utils/models.py:121-146): sum, sum of squares, per-neuron |z| < 1e-6 counts.
-// The dead test is one FMNMX per element; the (rare) counting path runs only when the chunk minimum trips it.
-__device__ __forceinline__ void chunk_stats(const float (&z)[16], float& s, float& q, uint32_t* dead_base) {
+// The dead test is one FMNMX per element; the counting path runs only when some row of the warp trips it, and counts with
+// warp ballots into a lane-distributed register (lane i: neuron 16c + i) -- no atomics in the loop: a unit that is dead for
+// every sample would otherwise serialise one global atomic per sample on a single address (measured: 50x slower kernel).
+__device__ __forceinline__ void chunk_stats(const float (&z)[16], bool valid, int lane, float& s, float& q, uint32_t& dead_cnt) {
     float mn = 1.0f;
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { s += z[i]; q = fmaf(z[i], z[i], q); mn = fminf(mn, fabsf(z[i])); }
-    if (mn < 1e-6f) {
+        for (int i = 0; i < 16; ++i) { s += z[i]; q = fmaf(z[i], z[i], q); mn = fminf(mn, fabsf(z[i])); }
+    }
+    if (__any_sync(0xffffffffu, mn < 1e-6f)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (fabsf(z[i]) < 1e-6f) atomicAdd(dead_base + i, 1u);
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t hits = __popc(__ballot_sync(0xffffffffu, valid && fabsf(z[i]) < 1e-6f));
+            if (lane == i) dead_cnt += hits;
+        }
     }
 }
 
@@ -264,14 +282,16 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     const int row = tid & 127;              // sample row of the tile == TMEM lane
     const int chunk = tid >> 7;             // 16-column chunk of the row this thread owns
     const int quad = warp & 3;              // TMEM lane quadrant of the warp
-    const bool row_owner = chunk == 0;      // does the per-row scalar work (gather, metrics, x^T / g^T)
+    const bool row_owner = chunk == 0;      // does the per-row gather and writes x^T / g^T
+
     const int A = m.A;
     const ParamOffsets po = param_offsets(m.D, 64, 64, m.A, m.has_value);
 
     // ---- one-time staging ------------------------------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, tcu::kTmemCols);
     if (tid == 0) {
-        mbar_init(&bars[tcu::BAR_FWD], 1); mbar_init(&bars[tcu::BAR_D], 1); mbar_init(&bars[tcu::BAR_W], 1); mbar_init(&bars[tcu::BAR_T], 1);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
     {
@@ -297,7 +317,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
         float4* z4 = reinterpret_cast<float4*>(smraw + tcu::oTH);
         for (int i = tid; i < (tcu::oW2 - tcu::oTH) / 16; i += tcu::kT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = tid; i < 4096; i += tcu::kT) Yhi[i] = 0.f;
-        if (tid < PM_N + 2) red[tid] = 0.0;
+        if (tid < PM_N + 8) red[tid] = 0.0;
     }
     __syncthreads();
     // transposed-store constants of this thread (sample column s = row): element (feature f, sample s) of a region sits at
@@ -309,7 +329,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     const int base_hi = (row >> 5) * (tcu::kHiSlab / 4) + (row & 3);
     const int base_lo = (row >> 5) * (tcu::kLoSlab / 4) + (row & 3);
     const int base_y = (row >> 5) * 512 + (row & 3);
-    if (row_owner) {
+    if (tid < 128) {
         TH[base_hi + 128 * 32 + xo[0]] = 1.0f;          // ones row behind S: db2 is column 64 of the dW2 accumulator
         Yhi[base_y + 7 * 32 + xo[7]] = 1.0f;            // ones row of x^T: db1 is column 7 of the tail accumulator
     }
@@ -323,74 +343,106 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     fence_after_sync();
     const uint32_t tmem = uniform(*tmem_slot);
     const uint32_t warp_u = uniform((uint32_t)warp);   // warp index the compiler knows to be uniform: single-UTCHMMA issue
+    const int64_t n_tiles = (b.n + tcu::kRows - 1) / tcu::kRows;
+    const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1: the launcher sizes the grid to the tiles
+
+    // ---- MMA-issuing warps ------------------------------------------------------------------------------------------------
+    // One issuing thread sustains one tcgen05.mma per ~60 cycles whatever the shape (probes/tc_rate.cu); two issuing warps with
+    // independent accumulator chains reach the tensor pipe's own rate (~33 cycles for M=128 N=64 K=8 tf32).
+    if (warp_u >= 16) {
+        const uint32_t sTH_ = smem_u32(TH), sTL_ = smem_u32(TL), sY_ = smem_u32(Yhi);
+        const uint32_t sW2_ = smem_u32(smraw + tcu::oW2), sW2T_ = smem_u32(smraw + tcu::oW2T);
+#pragma unroll 1
+        for (int it = -1; it < n_my; ++it) {
+            const bool has_cur = it >= 0, has_next = it + 1 < n_my;
+            const uint32_t cur = (uint32_t)it & 1u, nxt = cur ^ 1u;
+            const bool flush_now = it > 0 && (it % kFlushTiles) == 0;
+            const uint32_t acc_w = (has_cur && (it % kFlushTiles) != 0) ? 1u : 0u;      // dW2|db2 accumulator restarts after a flush
+            const uint32_t acc_t = (it == -1 || flush_now) ? 0u : 1u;                   // tail accumulator
+            if (has_cur) {
+                mbar_wait(&bars[tcu::RDY_0], cur);                   // completion index it
+                fence_after_sync();
+            }
+            if (warp_u == 16) {
+                if (has_cur && elect_one()) { issue_ts_64x64(tmem, tcu::cA + 128u * cur, sW2T_, tcu::cAcc + 64u * cur); mma_commit(&bars[tcu::BAR_D]); }   // dgrad(t)
+                if (has_next) {
+                    mbar_wait(&bars[tcu::RDY_1], nxt);               // completion index it+1
+                    fence_after_sync();
+                    if (elect_one()) { issue_ts_64x64(tmem, tcu::cA + 128u * nxt, sW2_, tcu::cAcc + 64u * nxt); mma_commit(&bars[tcu::BAR_FWD]); }  // fwd(u)
+                }
+            } else {
+                if (has_cur && elect_one()) { issue_dw2(tmem + tcu::cW2, sTH_, sTL_, acc_w); mma_commit(&bars[tcu::BAR_W]); }    // dW2 | db2 (t)
+                mbar_wait(&bars[tcu::RDY_2], nxt);                   // completion index it+1
+                fence_after_sync();
+                if (elect_one()) { issue_tail(tmem + tcu::cC, sTH_, sTL_, sY_, acc_t); mma_commit(&bars[tcu::BAR_T]); }          // dW1 | db1 | dWh
+            }
+        }
+        return;
+    }
+
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t sTH = smem_u32(TH), sTL = smem_u32(TL), sY = smem_u32(Yhi);
-    const uint32_t sW2 = smem_u32(smraw + tcu::oW2), sW2T = smem_u32(smraw + tcu::oW2T);
 
     float adv_mean = 0.f, adv_den = 1.f, ret_mean = 0.f, ret_den = 1.f;
     if (hp.normalize_adv) norm_consts(adv_mom, adv_mean, adv_den);
     if (hp.normalize_ret) norm_consts(ret_mom, ret_mean, ret_den);
     const float invB = 1.0f / (float)b.n;
 
-    float pm[PM_N];
-#pragma unroll
-    for (int i = 0; i < PM_N; ++i) pm[i] = 0.f;
-    float gsum[4] = {0.f, 0.f, 0.f, 0.f};   // head bias gradients (sum over this thread's samples; row owners only)
+    // Metric partial sums and head-bias gradients: quantity q (q < PM_N: metric partial q, PM_N + r: bias gradient r) is
+    // reduced by the chunk-(q & 3) warp of each row quadrant (all four compute the row's loss anyway): after a butterfly sum
+    // over the warp's 32 rows, lane q keeps it -> ONE register instead of 26, and the work is spread over all 16 warps.
+    float macc = 0.f;
     float zs0 = 0.f, zq0 = 0.f, zs1 = 0.f, zq1 = 0.f;
+    uint32_t dead0 = 0, dead1 = 0;          // dead-unit counts of this warp's rows: lane i holds neuron 16*chunk + i
 
     float* out = grad_partials + (size_t)blockIdx.x * pstride;    // this CTA's partial gradient vector (16 B aligned)
-    const int64_t n_tiles = (b.n + tcu::kRows - 1) / tcu::kRows;
-    const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1: the launcher sizes the grid to the tiles
-    // software-pipelined gather (row owners): the sample of the tile after next is loaded while two tiles are in flight, and
-    // its translated offset (offs[], written by gather_offsets_kernel) one tile earlier still, so no load waits on another
-    float nx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int n_a = 0;
-    float n_lp = 0.f, n_v = 0.f, n_adv = 0.f, n_ret = 0.f;
-    uint32_t n_off = 0;
-    auto load_off = [&](int64_t t) -> uint32_t {
-        const int64_t p = t * tcu::kRows + row;
-        return (t < n_tiles && p < b.n) ? __ldg(offs + p) : 0u;
-    };
-    // The gather is issued in four small bursts spread over the iteration (stage 0..3): a single burst of all 7 scattered
+    // Software-pipelined gather (stage s is issued by the row's chunk-s thread), register-free: cp.async copies the sample of the tile after next straight
+    // into a per-row staging slot in shared memory ([x0..x7, action, logp_old, value_old, adv, ret, offset of the following
+    // tile]); the owner reads its own slot one iteration later (cp.async.wait_all, no barrier: same thread).  Loads held in
+    // registers across the iteration get spilled by ptxas, which turns every prefetch into a synchronous load.
+    // The copies are issued in four small bursts spread over the iteration (stage 0..3): a single burst of all 7 scattered
     // loads of 128 rows (~900 sectors in flight) backs up the SM's L1TEX queue and stalls every warp's shared-memory loads
     // behind it for ~4000 cycles (measured with the clock64 trace); 128-256 sectors at a time do not.
-    int64_t pf_off = 0;
-    bool pf_ok = false;
+    float* stg = reinterpret_cast<float*>(smraw + tcu::oStage) + row * 16;
+    const uint32_t stg_s = smem_u32(stg);
+    uint32_t pf_off = 0;                    // translated offset of the tile being prefetched
     auto prefetch_stage = [&](int stage, int64_t t_next) {
+        const int64_t p = t_next * tcu::kRows + row;
+        const bool ok = t_next < n_tiles && p < b.n;
+        const int64_t off = (int64_t)pf_off;
         if (stage == 0) {
-#pragma unroll
-            for (int d = 0; d < 8; ++d) nx[d] = 0.f;
-            n_a = 0; n_lp = n_v = n_adv = n_ret = 0.f;
-            const int64_t p = t_next * tcu::kRows + row;
-            pf_ok = t_next < n_tiles && p < b.n;
-            pf_off = (int64_t)n_off;
-            if (pf_ok) {
-                const float* o = b.obs + pf_off * b.D;
+            if (ok) {
+                const float* o = b.obs + off * b.D;
                 if (D4) {
-                    if (b.D == 4) { const float4 v4 = __ldg(reinterpret_cast<const float4*>(o)); nx[0] = v4.x; nx[1] = v4.y; nx[2] = v4.z; nx[3] = v4.w; }
-                    else { const float2 v2 = __ldg(reinterpret_cast<const float2*>(o)); nx[0] = v2.x; nx[1] = v2.y; }
+                    if (b.D == 4) cp_async16(stg_s, o);
+                    else { cp_async8(stg_s, o); stg[2] = 0.f; stg[3] = 0.f; }
                 } else {
 #pragma unroll
-                    for (int d = 0; d < 7; ++d) if (d < b.D) nx[d] = __ldg(o + d);
+                    for (int d = 0; d < 8; ++d) { if (d < b.D) cp_async4(stg_s + 4 * d, o + d); else stg[d] = 0.f; }
                 }
+            } else {
+#pragma unroll
+                for (int d = 0; d < 13; ++d) stg[d] = 0.f;
             }
-            n_off = load_off(t_next + gridDim.x);
+            const int64_t p2 = (t_next + gridDim.x) * tcu::kRows + row;
+            if (t_next + gridDim.x < n_tiles && p2 < b.n) cp_async4(stg_s + 52, offs + p2); else stg[13] = 0.f;
         } else if (stage == 1) {
-            if (pf_ok) { n_a = __ldg(b.actions + pf_off); n_lp = __ldg(b.logp_old + pf_off); }
+            if (ok) { cp_async4(stg_s + 32, b.actions + off); cp_async4(stg_s + 36, b.logp_old + off); }
         } else if (stage == 2) {
-            if (pf_ok) { n_adv = __ldg(b.adv + pf_off); n_ret = __ldg(b.ret + pf_off); }
+            if (ok) { cp_async4(stg_s + 44, b.adv + off); cp_async4(stg_s + 48, b.ret + off); }
         } else {
-            if (ALGO == ALGO_PPO && pf_ok) n_v = __ldg(b.values_old + pf_off);
+            if (ok) { if (ALGO == ALGO_PPO) cp_async4(stg_s + 40, b.values_old + off); else stg[10] = 0.f; }
         }
     };
-    if (row_owner) {
-        n_off = load_off(blockIdx.x);
+    {
+        const int64_t p0 = (int64_t)blockIdx.x * tcu::kRows + row;
+        pf_off = p0 < b.n ? __ldg(offs + p0) : 0u;
 #pragma unroll
-        for (int st = 0; st < 4; ++st) prefetch_stage(st, blockIdx.x);
+        for (int st = 0; st < 4; ++st) if (chunk == st) prefetch_stage(st, blockIdx.x);
     }
 
     float g[4] = {0.f, 0.f, 0.f, 0.f};      // d(loss)/d(head outputs) of the tile entering its backward phase
     float xk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // its observation (layer 1 is recomputed in the backward phase)
+    uint32_t relu_mask2 = 0;                // relu: act'(h2) of the chunk, kept from the forward phase for the backward phase
     int s_a = 0;                            // gathered sample scalars of the tile in its forward phase (every chunk thread)
     float s_lp = 0.f, s_v = 0.f, s_adv = 0.f, s_ret = 0.f;
 #pragma unroll 1
@@ -403,8 +455,6 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
         const int64_t tile_u = blockIdx.x + (int64_t)(it + 1) * gridDim.x;
         const bool valid_u = has_next && (tile_u * tcu::kRows + row < b.n);
         const bool flush_now = it > 0 && (it % kFlushTiles) == 0;
-        const uint32_t acc_w = (has_cur && (it % kFlushTiles) != 0) ? 1u : 0u;      // dW2|db2 accumulator
-        const uint32_t acc_t = (it == -1 || flush_now) ? 0u : 1u;                   // tail accumulator
         uint32_t relu_mask = 0;             // ACT == relu: act'(h1) of the chunk; tanh: d1[]
         float d1[ACT == GS_ACT_RELU ? 1 : 16];
         // ---- B1(t): dz2 -> TMEM A[cur] and P, h1^T -> S, x^T -> Y ---------------------------------------------------------------
@@ -413,8 +463,10 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             float dz[16];
             {
                 float z[16];
-                tmem_ld16(lane_addr + acc_cur + 16 * chunk, z);
-                tmem_ld_wait();
+                if (ACT != GS_ACT_RELU) {                            // tanh: act'(h2) needs h2 again (relu: the mask kept from F2)
+                    tmem_ld16(lane_addr + acc_cur + 16 * chunk, z);
+                    tmem_ld_wait();
+                }
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,24 +475,24 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                         const float4 w = *reinterpret_cast<const float4*>(whs + r * 64 + 16 * chunk + i);
                         d.x = fmaf(g[r], w.x, d.x); d.y = fmaf(g[r], w.y, d.y); d.z = fmaf(g[r], w.z, d.z); d.w = fmaf(g[r], w.w, d.w);
                     }
-                    const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * chunk + i);
-                    dz[i] = d.x * act_bwd(act_fwd(z[i] + bb.x, ACT), ACT);
-                    dz[i + 1] = d.y * act_bwd(act_fwd(z[i + 1] + bb.y, ACT), ACT);
-                    dz[i + 2] = d.z * act_bwd(act_fwd(z[i + 2] + bb.z, ACT), ACT);
-                    dz[i + 3] = d.w * act_bwd(act_fwd(z[i + 3] + bb.w, ACT), ACT);
+                    if (ACT == GS_ACT_RELU) {
+                        dz[i] = ((relu_mask2 >> i) & 1u) ? d.x : 0.f;
+                        dz[i + 1] = ((relu_mask2 >> (i + 1)) & 1u) ? d.y : 0.f;
+                        dz[i + 2] = ((relu_mask2 >> (i + 2)) & 1u) ? d.z : 0.f;
+                        dz[i + 3] = ((relu_mask2 >> (i + 3)) & 1u) ? d.w : 0.f;
+                    } else {
+                        const float4 bb = *reinterpret_cast<const float4*>(b2s + 16 * chunk + i);
+                        dz[i] = d.x * act_bwd(act_fwd(z[i] + bb.x, ACT), ACT);
+                        dz[i + 1] = d.y * act_bwd(act_fwd(z[i + 1] + bb.y, ACT), ACT);
+                        dz[i + 2] = d.z * act_bwd(act_fwd(z[i + 2] + bb.z, ACT), ACT);
+                        dz[i + 3] = d.w * act_bwd(act_fwd(z[i + 3] + bb.w, ACT), ACT);
+                    }
                 }
             }
             chunk_to_tmem(lane_addr + a_cur, chunk, dz);             // A[cur] is free: fwd(t) completed
             GS_TR(16);
-            // the previous tail group reads P, S and Y: it must be done before they are rewritten
-            mbar_wait(&bars[tcu::BAR_T], ph);                        // completion index it (iteration -1 issued #0)
-            fence_after_sync();
-            if (flush_now) flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, it == kFlushTiles);
-            GS_TR(17);
-            chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
-            GS_TR(18);
             float z[16];
-            layer1_chunk<D4>(w1s, b1s, xk, chunk, z);
+            layer1_chunk<D4>(w1s, b1s, xk, chunk, z);                // h1(t) again: cheaper than keeping it for a whole tile
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 z[i] = act_fwd(z[i], ACT);
@@ -448,6 +500,13 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 else d1[ACT == GS_ACT_RELU ? 0 : i] = 1.0f - z[i] * z[i];
             }
             GS_TR(19);
+            // the previous tail group reads P, S and Y: it must be done before they are rewritten
+            mbar_wait(&bars[tcu::BAR_T], ph);                        // completion index it (iteration -1 issued #0)
+            fence_after_sync();
+            if (flush_now) flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, it == kFlushTiles);
+            GS_TR(17);
+            chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
+            GS_TR(18);
             chunk_to_transposed(Shi, Slo, base_hi, base_lo, xo, chunk, z);
             if (row_owner) {
 #pragma unroll
@@ -459,121 +518,49 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             }
         }
         // ---- owners: the next tile's gathered sample -> TMEM scratch (read by the row's other chunk threads) ----------------------
-        if (has_next && row_owner) {
-            float sx[16];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) sx[d] = nx[d];
-            sx[8] = __int_as_float(n_a); sx[9] = n_lp; sx[10] = n_v; sx[11] = n_adv; sx[12] = n_ret;
-            sx[13] = sx[14] = sx[15] = 0.f;
-            tmem_st16(lane_addr + tcu::cSX, sx);
-        }
+        if (has_next) cp_async_wait_all();                           // this thread's share of tile u's copies (issued an iteration ago) has landed
         GS_TR(1);
         tmem_st_wait();
         fence_proxy_async();
         fence_before_sync();
-        __syncthreads();                                                                                        // sync 1
+        tcu::compute_sync();                                                                                    // sync 1
+        if (has_cur && tid == 0) tcu::mbar_arrive(&bars[tcu::RDY_0]);    // -> dgrad(t)
         fence_after_sync();
         GS_TR(2);
-        if (has_cur) {
-            if (warp_u == 0 && elect_one()) { issue_ts_64x64(tmem, a_cur, sW2T, acc_cur); mma_commit(&bars[tcu::BAR_D]); }      // dgrad
-            if (warp_u == 1 && elect_one()) { issue_dw2(tmem + tcu::cW2, sTH, sTL, acc_w); mma_commit(&bars[tcu::BAR_W]); }     // dW2 | db2
-        }
-        GS_TR(3);
         // ---- F1(u): layer 1 -> h1 -> TMEM A[nxt] -------------------------------------------------------------------------------
         if (has_next) {
-            float sx[16];
-            tmem_ld16(lane_addr + tcu::cSX, sx);
-            tmem_ld_wait();
+            float sx[16];                                            // the row's staging slot, read by its four chunk threads
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (D4 && q == 1) continue;
+                const float4 v4 = *reinterpret_cast<const float4*>(stg + 4 * q);
+                sx[4 * q] = v4.x; sx[4 * q + 1] = v4.y; sx[4 * q + 2] = v4.z; sx[4 * q + 3] = v4.w;
+            }
+            if (D4) { sx[4] = sx[5] = sx[6] = sx[7] = 0.f; }
             s_a = __float_as_int(sx[8]); s_lp = sx[9]; s_v = sx[10]; s_adv = sx[11]; s_ret = sx[12];
+            pf_off = __float_as_uint(sx[13]);                        // offset of the tile after u: its copies start after sync 2
             GS_TR(20);
-            if (row_owner) prefetch_stage(0, tile_u + gridDim.x);
 #pragma unroll
             for (int d = 0; d < 8; ++d) xk[d] = sx[d];
             float z[16];
             GS_TR(21);
             layer1_chunk<D4>(w1s, b1s, xk, chunk, z);
             GS_TR(22);
-            if (TRACK && valid_u) chunk_stats(z, zs0, zq0, dead + 16 * chunk);
+            if (TRACK) chunk_stats(z, valid_u, lane, zs0, zq0, dead0);
             GS_TR(23);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i], ACT);
             chunk_to_tmem(lane_addr + a_nxt, chunk, z);              // A[nxt] is free: dgrad(t-1) completed
-            if (row_owner) prefetch_stage(1, tile_u + gridDim.x);
         }
         GS_TR(4);
         tmem_st_wait();
         fence_before_sync();
-        __syncthreads();                                                                                        // sync 2
+        tcu::compute_sync();                                                                                    // sync 2
+        if (has_next && tid == 0) tcu::mbar_arrive(&bars[tcu::RDY_1]);   // -> fwd(u), dW2(t)
         fence_after_sync();
         GS_TR(7);
-        if (has_next && warp_u == 2 && elect_one()) { issue_ts_64x64(tmem, a_nxt, sW2, acc_nxt); mma_commit(&bars[tcu::BAR_FWD]); }   // fwd(u)
-        GS_TR(8);
-        if (has_next && row_owner) prefetch_stage(2, tile_u + gridDim.x);
-        // ---- F2(u): z2 -> h2 -> this chunk's share of the head outputs -> TMEM scratch ------------------------------------------
-        if (has_next) {
-            mbar_wait(&bars[tcu::BAR_FWD], nxt);                     // completion index it+1
-            fence_after_sync();
-            GS_TR(9);
-            float z[16];
-            tmem_ld16(lane_addr + acc_nxt + 16 * chunk, z);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] += b2s[16 * chunk + i];
-            if (TRACK && valid_u) chunk_stats(z, zs1, zq1, dead + 64 + 16 * chunk);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i], ACT);
-            float o4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(whs + r * 64 + 16 * chunk + i);
-                    o4[r] = fmaf(z[i], w.x, o4[r]); o4[r] = fmaf(z[i + 1], w.y, o4[r]);
-                    o4[r] = fmaf(z[i + 2], w.z, o4[r]); o4[r] = fmaf(z[i + 3], w.w, o4[r]);
-                }
-            }
-            tmem_st4(lane_addr + tcu::cOP + 4 * chunk, o4);
-        }
-        GS_TR(10);
-        tmem_st_wait();
-        fence_before_sync();
-        __syncthreads();                                                                                        // sync 3
-        fence_after_sync();
-        GS_TR(11);
-        // ---- F3(u): loss and d(loss)/d(heads), redundantly by the four chunk threads of the row (metrics: the owner) -------------
-#pragma unroll
-        for (int r = 0; r < 4; ++r) g[r] = 0.f;
-        if (has_next) {
-            float op[16];
-            tmem_ld16(lane_addr + tcu::cOP, op);
-            tmem_ld_wait();
-            if (valid_u) {
-                float outv[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) outv[r] = bhs[r] + ((op[r] + op[4 + r]) + (op[8 + r] + op[12 + r]));
-                if (row_owner) {
-                    sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) gsum[r] += g[r];
-                } else {
-                    float pm_unused[PM_N];
-#pragma unroll
-                    for (int i = 0; i < PM_N; ++i) pm_unused[i] = 0.f;
-                    sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pm_unused);
-                }
-            }
-        }
-        if (row_owner) {                                             // Y is free: every thread waited for the previous tail in B1
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {                            // zeros when there is no next tile: the tail's heads block adds 0
-                const int idx = base_y + (8 + r) * 32 + xo[r];
-                const float gh = tf32_rn(g[r]);
-                Yhi[idx] = gh; Ylo[idx] = g[r] - gh;
-            }
-            if (has_next) prefetch_stage(3, tile_u + gridDim.x);
-        }
-        GS_TR(12);
-        // ---- dz1(t) = dh1 * act'(h1) -> dz1^T -> P ; h2^T(u) -> S -----------------------------------------------------------------
+        if (has_next && chunk == 0) prefetch_stage(0, tile_u + gridDim.x);   // every chunk thread has read the staging slots (sync 2)
+        // ---- dz1(t) = dh1 * act'(h1) -> dz1^T -> P, while fwd(u) runs ---------------------------------------------------------------
         if (has_cur) {
             float dz[16];
             mbar_wait(&bars[tcu::BAR_D], ph);
@@ -591,48 +578,127 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             GS_TR(14);
             chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
         }
+        // ---- F2(u): z2 -> h2 -> this chunk's share of the head outputs -> TMEM scratch ------------------------------------------
         if (has_next) {
+            mbar_wait(&bars[tcu::BAR_FWD], nxt);                     // completion index it+1
+            fence_after_sync();
+            GS_TR(9);
             float z[16];
-            tmem_ld16(lane_addr + acc_nxt + 16 * chunk, z);          // z2(u) is still in its accumulator: h2 is re-derived
+            tmem_ld16(lane_addr + acc_nxt + 16 * chunk, z);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = act_fwd(z[i] + b2s[16 * chunk + i], ACT);
-            chunk_to_transposed(Shi, Slo, base_hi, base_lo, xo, chunk, z);
+            for (int i = 0; i < 16; ++i) z[i] += b2s[16 * chunk + i];
+            if (TRACK) chunk_stats(z, valid_u, lane, zs1, zq1, dead1);
+            if (ACT == GS_ACT_RELU) relu_mask2 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                z[i] = act_fwd(z[i], ACT);
+                if (ACT == GS_ACT_RELU) relu_mask2 |= (z[i] > 0.f ? 1u : 0u) << i;
+            }
+            chunk_to_transposed(Shi, Slo, base_hi, base_lo, xo, chunk, z);   // S is free: this thread waited for dW2(t) above
+            float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(whs + r * 64 + 16 * chunk + i);
+                    o4[r] = fmaf(z[i], w.x, o4[r]); o4[r] = fmaf(z[i + 1], w.y, o4[r]);
+                    o4[r] = fmaf(z[i + 2], w.z, o4[r]); o4[r] = fmaf(z[i + 3], w.w, o4[r]);
+                }
+            }
+            tmem_st4(lane_addr + tcu::cOP + 4 * chunk, o4);
+            if (chunk == 1) prefetch_stage(1, tile_u + gridDim.x);
         }
+        GS_TR(10);
+        tmem_st_wait();
+        fence_before_sync();
+        tcu::compute_sync();                                                                                    // sync 3
+        fence_after_sync();
+        if (has_next && chunk == 2) prefetch_stage(2, tile_u + gridDim.x);
+        GS_TR(11);
+        // ---- F3(u): loss and d(loss)/d(heads), redundantly by the four chunk threads of the row (metrics: the owner) -------------
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[r] = 0.f;
+        float pl_keep[PM_N];                                         // this row's metric terms (dead code outside the metric owners)
+#pragma unroll
+        for (int i = 0; i < PM_N; ++i) pl_keep[i] = 0.f;
+        if (has_next) {
+            float op[16];
+            tmem_ld16(lane_addr + tcu::cOP, op);
+            tmem_ld_wait();
+            if (valid_u) {
+                float outv[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) outv[r] = bhs[r] + ((op[r] + op[4 + r]) + (op[8 + r] + op[12 + r]));
+                float pl[PM_N];                                      // this sample's metric terms (non-owners: dead code)
+#pragma unroll
+                for (int i = 0; i < PM_N; ++i) pl[i] = 0.f;
+                sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pl);
+#pragma unroll
+                for (int i = 0; i < PM_N; ++i) pl_keep[i] = pl[i];
+            }
+        }
+        if (has_next) {
+#pragma unroll
+            for (int i = 0; i < PM_N; ++i) {
+                if ((i & 3) != chunk) continue;
+                constexpr bool kPpoOnly[PM_N] = {false, true, false, true, true, true, true, true, true, false, false, false, false,
+                                                 false, false, false, false, false, false, false, false, false};
+                const bool z_stat = i == PM_Z0 || i == PM_Z0SQ || i == PM_Z1 || i == PM_Z1SQ;
+                const bool rf_only = i == PM_TGT || i == PM_TGT2 || i == PM_RETN || i == PM_RETN2;
+                if (z_stat || (ALGO == ALGO_PPO && rf_only) || (ALGO == ALGO_REINFORCE && kPpoOnly[i])) continue;
+                const float t = warp_sum(pl_keep[i]);
+                if (lane == i) macc += t;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (((PM_N + r) & 3) != chunk) continue;
+                const float t = warp_sum(g[r]);
+                if (lane == PM_N + r) macc += t;
+            }
+        }
+        if (row_owner) {                                             // Y is free: every thread waited for the previous tail in B1
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {                            // zeros when there is no next tile: the tail's heads block adds 0
+                const int idx = base_y + (8 + r) * 32 + xo[r];
+                const float gh = tf32_rn(g[r]);
+                Yhi[idx] = gh; Ylo[idx] = g[r] - gh;
+            }
+        }
+        if (has_next && chunk == 3) prefetch_stage(3, tile_u + gridDim.x);
+        GS_TR(12);
         GS_TR(15);
         fence_proxy_async();
         fence_before_sync();
-        __syncthreads();                                                                                        // sync 4
+        tcu::compute_sync();                                                                                    // sync 4
+        if (tid == 0) tcu::mbar_arrive(&bars[tcu::RDY_2]);               // -> tail(t,u)
         fence_after_sync();
-        if (warp_u == 3 && elect_one()) { issue_tail(tmem + tcu::cC, sTH, sTL, sY, acc_t); mma_commit(&bars[tcu::BAR_T]); }     // dW1 | db1 | dWh
     }
     // ---- drain: wait for the last tail group and flush what the TMEM accumulators still hold --------------------------------
     mbar_wait(&bars[tcu::BAR_T], (uint32_t)n_my & 1u);               // completion index n_my
     fence_after_sync();
     flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, n_my <= kFlushTiles);
     // ---- block reductions through shared-memory atomics: head biases (4 floats) and the metric partials (PM_N doubles) ------
-    float* fr = reinterpret_cast<float*>(red + PM_N);
-    if (TRACK) { pm[PM_Z0] = zs0; pm[PM_Z0SQ] = zq0; pm[PM_Z1] = zs1; pm[PM_Z1SQ] = zq1; }
-    if (row_owner || TRACK) {
-#pragma unroll
-        for (int i = 0; i < PM_N; ++i) {
-            const double v = warp_sum((double)pm[i]);
-            if (lane == 0 && v != 0.0) atomicAdd(red + i, v);
-        }
+    float* fr = reinterpret_cast<float*>(red + PM_N);            // [4 quadrants][4 heads] bias-gradient partials
+    if (lane < PM_N + 4 && (lane & 3) == chunk) {
+        if (lane < PM_N) { if (macc != 0.f) atomicAdd(red + lane, (double)macc); }
+        else fr[quad * 4 + (lane - PM_N)] = macc;
     }
-    if (row_owner) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float sgm = warp_sum(gsum[r]);
-            if (lane == 0) atomicAdd(fr + r, sgm);
+    if (TRACK) {
+        const double a0 = warp_sum((double)zs0), a1 = warp_sum((double)zq0), a2 = warp_sum((double)zs1), a3 = warp_sum((double)zq1);
+        if (lane == 0) { atomicAdd(red + PM_Z0, a0); atomicAdd(red + PM_Z0SQ, a1); atomicAdd(red + PM_Z1, a2); atomicAdd(red + PM_Z1SQ, a3); }
+        if (lane < 16) {
+            if (dead0) atomicAdd(dead + 16 * chunk + lane, dead0);
+            if (dead1) atomicAdd(dead + 64 + 16 * chunk + lane, dead1);
         }
     }
     fence_before_sync();
-    __syncthreads();
+    tcu::compute_sync();
     if (tid < PM_N) metric_partials[(size_t)blockIdx.x * PM_N + tid] = red[tid];
     if (tid < 4) {
-        if (tid < A) out[po.bp + tid] = fr[tid];
-        else if (tid == A && m.has_value) out[po.bv] = fr[tid];
+        const float sgm = (fr[tid] + fr[4 + tid]) + (fr[8 + tid] + fr[12 + tid]);     // fixed order: deterministic
+        if (tid < A) out[po.bp + tid] = sgm;
+        else if (tid == A && m.has_value) out[po.bv] = sgm;
     }
     if (warp == 0) tmem_dealloc(tmem, tcu::kTmemCols);
 }
@@ -664,7 +730,7 @@ template int launch_update_tc<ALGO_REINFORCE>(const MlpDev&, const BatchDev&, co
 }  // namespace gs
 
 #ifdef GS_TC_TRACE
-extern "C" int gs_debug_tc_trace(long long* host_out /* [16][24] */) {
-    return (int)cudaMemcpyFromSymbol(host_out, gs::g_tc_trace, sizeof(long long) * 384);
+extern "C" int gs_debug_tc_trace(long long* host_out /* [18][24] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_tc_trace, sizeof(long long) * 432);
 }
 #endif

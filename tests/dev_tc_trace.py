@@ -23,9 +23,9 @@ hp = N.GsPpoHparams(); hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef,
 for _ in range(3):
     E.update_step("ppo", E.dev_params(p), batch, hp)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 384)()
+buf = (ctypes.c_longlong * 432)()
 rc = N.lib().gs_debug_tc_trace(buf)
-tr = np.array(buf[:]).reshape(16, 24)
+tr = np.array(buf[:]).reshape(18, 24)[:16]
 t0 = tr[:, 0].min()
 order = [0, 16, 17, 18, 19, 1, 2, 3, 20, 21, 22, 23, 4, 7, 8, 9, 10, 11, 12, 13, 14, 15]
 names = ["top", "B1 done", "sync1", "issued A", "F1 done", "", "", "sync2", "issued fwd", "BAR_FWD ok", "F2 done", "sync3", "F3 done",
