@@ -261,11 +261,27 @@ def kernel_rooflines(agent, cfg, dev):
     hd = tuple(cfg.hidden_dims)
     flops = FLOP_PER_SAMPLE_PASS.get(hd, 27264) * agent.local_batch_size
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    out["update"] = {"kernel": "update_kernel<64,64,128,PPO> (gs_ppo_step)", "bound": "fp32_simt", "achieved": flops / t / 1e12,
-                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / fp32_peak, "traffic": None,
-                     "note": "fp32 FMA-pipe kernel (no tensor cores yet): peak = 148 SM x 128 FMA x 2 x sm_max_mhz; "
-                             f"vs measured bf16 tensor peak {peaks['bf16_tflops']:.0f} TF/s this is {flops / t / 1e12 / peaks['bf16_tflops']:.4f}",
-                     "algorithmic_flop_per_launch": flops, "avg_launch_s": t}
+    tensor_path = hd == (64, 64) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
+    if tensor_path:
+        # 144 tcgen05.mma (K=8 tf32) per 128-sample tile; two issuing warps sustain one MMA per ~33 cycles (probes/tc_rate.cu)
+        tiles_per_sm = -(-(agent.local_batch_size // 128) // 148)
+        mma_floor_s = tiles_per_sm * 144 * 33.0 / (peaks["sm_max_mhz"] * 1e6)
+        out["update"] = {"kernel": "update_tc_kernel<PPO> (gs_ppo_step: tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)", "bound": "tensor",
+                         "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"],
+                         "traffic": None,
+                         "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the 64x64 MLP) / time of the whole gs_ppo_step call "
+                                 "(gather pass + update kernel + partial reduction + metric finalisation); peak = measured dense bf16. "
+                                 "fp32 parity (1e-4) costs 3 tf32 MMAs per product, and K=8 tf32 MMAs with N<=72 are bound by a per-instruction "
+                                 f"floor, not by math: tensor-pipe floor of this launch {mma_floor_s * 1e3:.3f} ms; the rest is SIMT work between the "
+                                 f"MMAs (profiles/). Same arithmetic on the FMA pipe (GS_UPDATE_IMPL=simt): 1.09 ms; fp32 FMA peak {fp32_peak:.1f} TF/s",
+                         "algorithmic_flop_per_launch": flops, "avg_launch_s": t, "tensor_pipe_floor_s": mma_floor_s,
+                         "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}
+    else:
+        out["update"] = {"kernel": f"update_kernel<{hd}> (gs_ppo_step, fp32 FMA pipe)", "bound": "tensor", "achieved": flops / t / 1e12,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                         "note": f"fp32 FMA-pipe kernel: fp32 FMA peak {fp32_peak:.1f} TF/s = 148 SM x 128 FMA x 2 x sm_max_mhz, of which "
+                                 f"{flops / t / 1e12 / fp32_peak:.3f}",
+                         "algorithmic_flop_per_launch": flops, "avg_launch_s": t, "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}
     # GAE kernel
     b = col._buffer
     T, n = int(cfg.n_steps), agent.local_n_envs
@@ -384,7 +400,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -398,7 +414,11 @@ def main():
     ap.add_argument("--track-activations", type=int, default=1)
     ap.add_argument("--cpu-envs", type=int, default=512, help="envs of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -188,7 +188,9 @@ __device__ __forceinline__ void tile_tn(float (&acc)[8][4], const float* G, int 
 // ---- activation statistics of the hooked Linear outputs (utils/models.py:121-146) --------------------------------
 struct ActStats {
     float sum[2], sumsq[2];   // per-thread partials of z and z^2 for backbone.0 / backbone.2
-    uint32_t* dead;           // global [H1 + H2] counters of |z| < 1e-6 (integer atomics: deterministic)
+    uint32_t* dead;           // per-CTA shared-memory [H1 + H2] counters of |z| < 1e-6, flushed once to the global counters
+                              // (integer atomics: deterministic; never one global atomic per sample: a unit that is dead for
+                              // the whole batch would serialise them on a single address)
 };
 
 // ---- forward -------------------------------------------------------------------------------------------------
@@ -208,16 +210,18 @@ __device__ __forceinline__ void forward_layer1(float* sm, int act, int valid_row
         for (int i = 0; i < 4; ++i) {
             const int n = nc * 64 + tx + 16 * i;
             const float b = sm[C::oB1 + n];
+            uint32_t n_dead = 0;
 #pragma unroll
             for (int j = 0; j < C::TS; ++j) {
                 const int s = ty * C::TS + j;
                 const float z = acc[j][i] + b;
                 if (TRACK && s < valid_rows) {
                     st->sum[0] += z; st->sumsq[0] = fmaf(z, z, st->sumsq[0]);
-                    if (fabsf(z) < 1e-6f) atomicAdd(st->dead + n, 1u);
+                    n_dead += fabsf(z) < 1e-6f ? 1u : 0u;
                 }
                 sm[C::oA1 + s * C::LD1 + n] = act_fwd(z, act);
             }
+            if (TRACK && n_dead) atomicAdd(st->dead + n, n_dead);
         }
     }
 }
@@ -246,16 +250,18 @@ __device__ __forceinline__ void forward_layer2(float* sm, const MlpDev& m, int v
         for (int i = 0; i < 4; ++i) {
             const int n = nc * 64 + tx + 16 * i;
             const float b = sm[C::oB2 + n];
+            uint32_t n_dead = 0;
 #pragma unroll
             for (int j = 0; j < C::TS; ++j) {
                 const int s = ty * C::TS + j;
                 const float z = acc[j][i] + b;
                 if (TRACK && s < valid_rows) {
                     st->sum[1] += z; st->sumsq[1] = fmaf(z, z, st->sumsq[1]);
-                    if (fabsf(z) < 1e-6f) atomicAdd(st->dead + C::H1 + n, 1u);
+                    n_dead += fabsf(z) < 1e-6f ? 1u : 0u;
                 }
                 sm[C::oA2 + s * C::LD2 + n] = act_fwd(z, m.act);
             }
+            if (TRACK && n_dead) atomicAdd(st->dead + C::H1 + n, n_dead);
         }
     }
 }

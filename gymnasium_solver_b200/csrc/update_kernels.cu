@@ -54,7 +54,9 @@ update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom
     for (int i = 0; i < PM_N; ++i) pm[i] = 0.f;
     ActStats st;
     st.sum[0] = st.sum[1] = st.sumsq[0] = st.sumsq[1] = 0.f;
-    st.dead = dead;
+    __shared__ uint32_t s_dead[512];            // H1 + H2 <= 512
+    for (int i = tid; i < C::H1 + C::H2; i += kThreads) s_dead[i] = 0u;
+    st.dead = s_dead;
 
     const int64_t n_tiles = (b.n + S - 1) / S;
     __syncthreads();
@@ -294,6 +296,12 @@ update_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom
         for (int i = tid; i < P; i += kThreads) out[i] = gsm[i];
     }
 
+    // ---- dead-unit counts of this CTA: one global integer atomic per unit --------------------------------------------------
+    if (TRACK) {
+        __syncthreads();
+        for (int i = tid; i < C::H1 + C::H2; i += kThreads)
+            if (s_dead[i]) atomicAdd(dead + i, s_dead[i]);
+    }
     // ---- metric partials: warp shuffle, then one cross-warp pass through shared memory ---------------------------------
     if (TRACK) { pm[PM_Z0] = st.sum[0]; pm[PM_Z0SQ] = st.sumsq[0]; pm[PM_Z1] = st.sum[1]; pm[PM_Z1SQ] = st.sumsq[1]; }
     __syncthreads();

@@ -71,9 +71,11 @@ constexpr int oWH = oB2 + 256;          // [4][64]
 constexpr int oBH = oWH + 1024;         // [4]
 constexpr int oBar = oBH + 16;          // 7 mbarriers
 constexpr int oTmem = oBar + 64;
-constexpr int oRed = oTmem + 16;        // PM_N doubles + 16 floats (block reductions)
-constexpr int oStage = oRed + 256;      // gather staging [128 rows][16] fp32 (cp.async destination)
-constexpr int kSmemBytes = oStage + 128 * 64;
+constexpr int oRed = oTmem + 16;        // PM_N doubles + 16 floats (block reductions) + 8 floats (normalisation constants, 1/B)
+constexpr int oStage = oRed + 320;      // gather staging [128 rows][16] fp32 (cp.async destination)
+static_assert(PM_N * 8 + 16 * 4 + 8 * 4 <= 320, "reduction scratch");
+constexpr int oScal1 = oStage + 128 * 64;   // second buffer of the 5 sample scalars [128 rows][5] (odd tiles; even tiles use slots 8..12 of the row)
+constexpr int kSmemBytes = oScal1 + 128 * 20;
 static_assert(oTL % 1024 == 0 && oW2 % 1024 == 0 && oY % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM columns: A[b] = 128*b (hi +0, lo +64); acc[b] = 256 + 64*b; dW2|db2 (72 used of 80); tail accumulator; per-row scratch
@@ -212,7 +214,8 @@ __device__ __forceinline__ void issue_tail(uint32_t tmem_acc, uint32_t th, uint3
 //   tail (M=128):   lane = row; rows 0..63: cols 0..6 dW1[row][d], col 7 db1[row]; rows 64..127: cols 8+r dWh[r][row-64].
 constexpr int kFlushTiles = 8;
 __device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int chunk, int lane, int row, int D, int A, int has_value,
-                                            const ParamOffsets& po, float* __restrict__ out, bool first) {
+                                            float* __restrict__ out, bool first) {
+    const ParamOffsets po = param_offsets(D, 64, 64, A, has_value);
     const int mrow = quad * 16 + (lane & 15);
     const bool owner = lane < 16;
     float4* dst = reinterpret_cast<float4*>(out + po.w2 + mrow * 64 + 16 * chunk);
@@ -285,7 +288,6 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     const bool row_owner = chunk == 0;      // does the per-row gather and writes x^T / g^T
 
     const int A = m.A;
-    const ParamOffsets po = param_offsets(m.D, 64, 64, m.A, m.has_value);
 
     // ---- one-time staging ------------------------------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, tcu::kTmemCols);
@@ -382,10 +384,15 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
 
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 
-    float adv_mean = 0.f, adv_den = 1.f, ret_mean = 0.f, ret_den = 1.f;
-    if (hp.normalize_adv) norm_consts(adv_mom, adv_mean, adv_den);
-    if (hp.normalize_ret) norm_consts(ret_mom, ret_mean, ret_den);
-    const float invB = 1.0f / (float)b.n;
+    // normalisation constants and 1/B live in shared memory (read once per tile, uniformly): five fewer long-lived registers
+    float* ncs = reinterpret_cast<float*>(red + PM_N) + 16;
+    if (tid == 0) {
+        float adv_mean = 0.f, adv_den = 1.f, ret_mean = 0.f, ret_den = 1.f;
+        if (hp.normalize_adv) norm_consts(adv_mom, adv_mean, adv_den);
+        if (hp.normalize_ret) norm_consts(ret_mom, ret_mean, ret_den);
+        ncs[0] = adv_mean; ncs[1] = adv_den; ncs[2] = ret_mean; ncs[3] = ret_den; ncs[4] = 1.0f / (float)b.n;
+    }
+    tcu::compute_sync();
 
     // Metric partial sums and head-bias gradients: quantity q (q < PM_N: metric partial q, PM_N + r: bias gradient r) is
     // reduced by the chunk-(q & 3) warp of each row quadrant (all four compute the row's loss anyway): after a butterfly sum
@@ -405,7 +412,11 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     float* stg = reinterpret_cast<float*>(smraw + tcu::oStage) + row * 16;
     const uint32_t stg_s = smem_u32(stg);
     uint32_t pf_off = 0;                    // translated offset of the tile being prefetched
-    auto prefetch_stage = [&](int stage, int64_t t_next) {
+    float* sc1 = reinterpret_cast<float*>(smraw + tcu::oScal1) + row * 5 - 8;   // indexed like stg: scalars at [8..12]
+    const uint32_t sc1_s = smem_u32(sc1);
+    auto prefetch_stage = [&](int stage, int64_t t_next, uint32_t par = 0) {   // par: parity of the tile's position in this CTA's sequence
+        float* sc = par ? sc1 : stg;
+        const uint32_t sc_s = par ? sc1_s : stg_s;
         const int64_t p = t_next * tcu::kRows + row;
         const bool ok = t_next < n_tiles && p < b.n;
         const int64_t off = (int64_t)pf_off;
@@ -421,30 +432,31 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 }
             } else {
 #pragma unroll
-                for (int d = 0; d < 13; ++d) stg[d] = 0.f;
+                for (int d = 0; d < 8; ++d) stg[d] = 0.f;
             }
             const int64_t p2 = (t_next + gridDim.x) * tcu::kRows + row;
             if (t_next + gridDim.x < n_tiles && p2 < b.n) cp_async4(stg_s + 52, offs + p2); else stg[13] = 0.f;
         } else if (stage == 1) {
-            if (ok) { cp_async4(stg_s + 32, b.actions + off); cp_async4(stg_s + 36, b.logp_old + off); }
+            if (ok) { cp_async4(sc_s + 32, b.actions + off); cp_async4(sc_s + 36, b.logp_old + off); }
+            else { sc[8] = 0.f; sc[9] = 0.f; }
         } else if (stage == 2) {
-            if (ok) { cp_async4(stg_s + 44, b.adv + off); cp_async4(stg_s + 48, b.ret + off); }
+            if (ok) { cp_async4(sc_s + 44, b.adv + off); cp_async4(sc_s + 48, b.ret + off); }
+            else { sc[11] = 0.f; sc[12] = 0.f; }
         } else {
-            if (ok) { if (ALGO == ALGO_PPO) cp_async4(stg_s + 40, b.values_old + off); else stg[10] = 0.f; }
+            if (ok && ALGO == ALGO_PPO) cp_async4(sc_s + 40, b.values_old + off); else sc[10] = 0.f;
         }
     };
     {
         const int64_t p0 = (int64_t)blockIdx.x * tcu::kRows + row;
         pf_off = p0 < b.n ? __ldg(offs + p0) : 0u;
 #pragma unroll
-        for (int st = 0; st < 4; ++st) if (chunk == st) prefetch_stage(st, blockIdx.x);
+#pragma unroll
+        for (int st = 0; st < 4; ++st) if (chunk == st) prefetch_stage(st, blockIdx.x, 0u);
     }
 
     float g[4] = {0.f, 0.f, 0.f, 0.f};      // d(loss)/d(head outputs) of the tile entering its backward phase
     float xk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // its observation (layer 1 is recomputed in the backward phase)
     uint32_t relu_mask2 = 0;                // relu: act'(h2) of the chunk, kept from the forward phase for the backward phase
-    int s_a = 0;                            // gathered sample scalars of the tile in its forward phase (every chunk thread)
-    float s_lp = 0.f, s_v = 0.f, s_adv = 0.f, s_ret = 0.f;
 #pragma unroll 1
     for (int it = -1; it < n_my; ++it) {
         const bool has_cur = it >= 0, has_next = it + 1 < n_my;
@@ -491,6 +503,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             }
             chunk_to_tmem(lane_addr + a_cur, chunk, dz);             // A[cur] is free: fwd(t) completed
             GS_TR(16);
+
             float z[16];
             layer1_chunk<D4>(w1s, b1s, xk, chunk, z);                // h1(t) again: cheaper than keeping it for a whole tile
 #pragma unroll
@@ -503,7 +516,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             // the previous tail group reads P, S and Y: it must be done before they are rewritten
             mbar_wait(&bars[tcu::BAR_T], ph);                        // completion index it (iteration -1 issued #0)
             fence_after_sync();
-            if (flush_now) flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, it == kFlushTiles);
+            if (flush_now) flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, out, it == kFlushTiles);
             GS_TR(17);
             chunk_to_transposed(Phi, Plo, base_hi, base_lo, xo, chunk, dz);
             GS_TR(18);
@@ -517,7 +530,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 }
             }
         }
-        // ---- owners: the next tile's gathered sample -> TMEM scratch (read by the row's other chunk threads) ----------------------
+        // ---- the gathered sample of tile u must have landed before the row's chunk threads read the staging slot -------------------
         if (has_next) cp_async_wait_all();                           // this thread's share of tile u's copies (issued an iteration ago) has landed
         GS_TR(1);
         tmem_st_wait();
@@ -532,12 +545,11 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             float sx[16];                                            // the row's staging slot, read by its four chunk threads
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (D4 && q == 1) continue;
+                if ((D4 && q == 1) || q == 2) continue;              // the sample scalars (8..12) are read in F3
                 const float4 v4 = *reinterpret_cast<const float4*>(stg + 4 * q);
                 sx[4 * q] = v4.x; sx[4 * q + 1] = v4.y; sx[4 * q + 2] = v4.z; sx[4 * q + 3] = v4.w;
             }
             if (D4) { sx[4] = sx[5] = sx[6] = sx[7] = 0.f; }
-            s_a = __float_as_int(sx[8]); s_lp = sx[9]; s_v = sx[10]; s_adv = sx[11]; s_ret = sx[12];
             pf_off = __float_as_uint(sx[13]);                        // offset of the tile after u: its copies start after sync 2
             GS_TR(20);
 #pragma unroll
@@ -607,14 +619,14 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 }
             }
             tmem_st4(lane_addr + tcu::cOP + 4 * chunk, o4);
-            if (chunk == 1) prefetch_stage(1, tile_u + gridDim.x);
+            if (chunk == 1) prefetch_stage(1, tile_u + gridDim.x, cur);
         }
         GS_TR(10);
         tmem_st_wait();
         fence_before_sync();
         tcu::compute_sync();                                                                                    // sync 3
         fence_after_sync();
-        if (has_next && chunk == 2) prefetch_stage(2, tile_u + gridDim.x);
+        if (has_next && chunk == 2) prefetch_stage(2, tile_u + gridDim.x, cur);
         GS_TR(11);
         // ---- F3(u): loss and d(loss)/d(heads), redundantly by the four chunk threads of the row (metrics: the owner) -------------
 #pragma unroll
@@ -633,7 +645,8 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 float pl[PM_N];                                      // this sample's metric terms (non-owners: dead code)
 #pragma unroll
                 for (int i = 0; i < PM_N; ++i) pl[i] = 0.f;
-                sample_loss<ALGO>(outv, A, s_a, s_lp, s_v, s_adv, s_ret, hp, adv_mean, adv_den, ret_mean, ret_den, invB, g, pl);
+                const float* sc = nxt ? sc1 : stg;                   // tile u's scalars: buffer of its parity
+                sample_loss<ALGO>(outv, A, __float_as_int(sc[8]), sc[9], sc[10], sc[11], sc[12], hp, ncs[0], ncs[1], ncs[2], ncs[3], ncs[4], g, pl);
 #pragma unroll
                 for (int i = 0; i < PM_N; ++i) pl_keep[i] = pl[i];
             }
@@ -665,7 +678,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 Yhi[idx] = gh; Ylo[idx] = g[r] - gh;
             }
         }
-        if (has_next && chunk == 3) prefetch_stage(3, tile_u + gridDim.x);
+        if (has_next && chunk == 3) prefetch_stage(3, tile_u + gridDim.x, cur);
         GS_TR(12);
         GS_TR(15);
         fence_proxy_async();
@@ -677,7 +690,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     // ---- drain: wait for the last tail group and flush what the TMEM accumulators still hold --------------------------------
     mbar_wait(&bars[tcu::BAR_T], (uint32_t)n_my & 1u);               // completion index n_my
     fence_after_sync();
-    flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, po, out, n_my <= kFlushTiles);
+    flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, out, n_my <= kFlushTiles);
     // ---- block reductions through shared-memory atomics: head biases (4 floats) and the metric partials (PM_N doubles) ------
     float* fr = reinterpret_cast<float*>(red + PM_N);            // [4 quadrants][4 heads] bias-gradient partials
     if (lane < PM_N + 4 && (lane & 3) == chunk) {
@@ -696,6 +709,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     tcu::compute_sync();
     if (tid < PM_N) metric_partials[(size_t)blockIdx.x * PM_N + tid] = red[tid];
     if (tid < 4) {
+        const ParamOffsets po = param_offsets(m.D, 64, 64, m.A, m.has_value);
         const float sgm = (fr[tid] + fr[4 + tid]) + (fr[8 + tid] + fr[12 + tid]);     // fixed order: deterministic
         if (tid < A) out[po.bp + tid] = sgm;
         else if (tid == A && m.has_value) out[po.bv] = sgm;
