@@ -34,11 +34,13 @@ class PPOAgent(BaseAgent):
         L = N.lib()
         with torch.cuda.device(self.device):
             st = N.stream()
-            if hp.normalize_adv:
+            adv_mom = None                       # one rank: the step takes the minibatch moments itself, in its gather pass
+            if hp.normalize_adv and self.world_size > 1:
                 self._adv_mom.zero_()
                 N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._adv_mom), st))
                 allreduce_moments(self._adv_mom, self.world_size)   # statistics of the GLOBAL minibatch (W-invariant update)
-            N.check(L.gs_ppo_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(self._adv_mom), N.ptr(model.flat_grads),
+                adv_mom = self._adv_mom
+            N.check(L.gs_ppo_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(adv_mom), N.ptr(model.flat_grads),
                                   N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
         early_stop = False
         if cfg.target_kl is not None:       # the only per-minibatch host sync, and only when KL early stop is enabled

@@ -35,13 +35,15 @@ class REINFORCEAgent(BaseAgent):
         L = N.lib()
         with torch.cuda.device(self.device):
             st = N.stream()
-            if hp.normalize_returns or hp.normalize_adv:
+            ret_mom = adv_mom = None             # one rank: the step takes the minibatch moments itself, in its gather pass
+            if (hp.normalize_returns or hp.normalize_adv) and self.world_size > 1:
                 self._mom.zero_()
                 if hp.normalize_returns:
                     N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.ret, N.ptr(self._mom[0]), st))
                 if hp.normalize_adv:
                     N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._mom[1]), st))
                 allreduce_moments(self._mom, self.world_size)
-            N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(self._mom[0]), N.ptr(self._mom[1]),
+                ret_mom, adv_mom = self._mom[0], self._mom[1]
+            N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(ret_mom), N.ptr(adv_mom),
                                         N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
         return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=False)

@@ -332,9 +332,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     grads[i] = s;
 }
 
-__global__ void finalize_metrics_kernel(const double* __restrict__ partials, int n_cta, int algo, int H1, int H2, int track,
-                                        float vf_coef, float ent_coef, int normalize_adv, int normalize_ret,
-                                        const uint32_t* __restrict__ dead, double* __restrict__ metrics) {
+__device__ __forceinline__ void finalize_metrics_body(const double* __restrict__ partials, int n_cta, int algo, int H1, int H2, int track,
+                                                      float vf_coef, float ent_coef, int normalize_adv, int normalize_ret,
+                                                      const uint32_t* __restrict__ dead, double* __restrict__ metrics) {
     __shared__ double tot[PM_N];
     __shared__ double dead_stats[4];
     const int tid = threadIdx.x;
@@ -405,6 +405,24 @@ __global__ void finalize_metrics_kernel(const double* __restrict__ partials, int
     }
 }
 
+// One launch folds the per-CTA partials: blocks 0 .. n_red-1 sum the partial gradient vectors in CTA order (deterministic),
+// the last block turns the metric partials into the metric vector.
+__global__ void reduce_and_finalize_kernel(const float* __restrict__ partials, int n_cta, int64_t P, int64_t pstride, float* __restrict__ grads,
+                                           const double* __restrict__ metric_partials, int algo, int H1, int H2, int track, float vf_coef,
+                                           float ent_coef, int normalize_adv, int normalize_ret, const uint32_t* __restrict__ dead,
+                                           double* __restrict__ metrics) {
+    if (blockIdx.x == gridDim.x - 1) {
+        finalize_metrics_body(metric_partials, n_cta, algo, H1, H2, track, vf_coef, ent_coef, normalize_adv, normalize_ret, dead, metrics);
+        return;
+    }
+    if (!partials) return;                      // atomic-accumulation configurations have no partial vectors
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * pstride + i];
+    grads[i] = s;
+}
+
 // ---- minibatch moments of a rollout field (advantage / return batch normalisation) -------------------------------------
 __global__ void batch_moments_kernel(BatchDev b, const float* __restrict__ field, double* __restrict__ out) {
     __shared__ double scratch[32];
@@ -453,6 +471,38 @@ __global__ void clip_scale_kernel(float* __restrict__ g, int64_t P, const double
     if (coef < 1.0) {
         const float c = (float)coef;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) g[i] *= c;
+    }
+}
+
+// grad norms + clip of a small parameter vector in ONE block: group sums of squares in a fixed order, then the scaling pass
+__global__ void __launch_bounds__(1024) clip_grad_norm_kernel(float* __restrict__ g, ParamOffsets po, float max_norm, double* __restrict__ metrics) {
+    __shared__ double scratch[32];
+    __shared__ double sq[3];
+    double part[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < po.total; i += blockDim.x) {
+        const double v = (double)g[i];
+        const int grp = i < po.wp ? 0 : (i < po.wv ? 1 : 2);
+        part[grp] += v * v;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double t = block_sum(part[k], scratch);
+        if (threadIdx.x == 0) sq[k] = t;
+    }
+    __syncthreads();
+    const double total = sqrt(sq[0] + sq[1] + sq[2]);
+    double coef = 1.0;      // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total + 1e-6), clamped to 1
+    if (max_norm > 0.f) { coef = (double)max_norm / (total + 1e-6); coef = coef > 1.0 ? 1.0 : coef; }
+    if (threadIdx.x == 0 && metrics) {
+        metrics[GS_M_GRAD_NORM_ALL] = total;
+        metrics[GS_M_GRAD_NORM_BACKBONE] = sqrt(sq[0]);
+        metrics[GS_M_GRAD_NORM_POLICY] = sqrt(sq[1]);
+        metrics[GS_M_GRAD_NORM_VALUE] = sqrt(sq[2]);
+        metrics[GS_M_CLIP_COEF] = coef;
+    }
+    if (coef < 1.0) {
+        const float c = (float)coef;
+        for (int64_t i = threadIdx.x; i < po.total; i += blockDim.x) g[i] *= c;
     }
 }
 
@@ -539,9 +589,26 @@ int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool 
 // Sample-id translation of the whole minibatch in one pass: offs[pos] = time-major offset of minibatch position pos.  The
 // keyed Feistel walk + env-major -> time-major division is a ~1000-instruction dependent chain per sample (cycle walking
 // diverges inside a warp); done here it is spread over the whole GPU instead of sitting on the update kernel's critical path.
-__global__ void gather_offsets_kernel(BatchDev b, uint32_t* __restrict__ offs) {
+// With f0 / f1 given it also accumulates {sum, sum of squares, count} of those rollout fields over the minibatch (the batch
+// normalisation moments of gs_batch_moments) into mom[0..2] / mom[3..5]: one pass instead of two over the permutation.
+__global__ void gather_offsets_kernel(BatchDev b, uint32_t* __restrict__ offs, const float* __restrict__ f0, const float* __restrict__ f1,
+                                      double* __restrict__ mom) {
+    __shared__ double scratch[32];
     const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos < b.n) offs[pos] = (uint32_t)sample_offset(b, pos);
+    int64_t off = 0;
+    if (pos < b.n) { off = sample_offset(b, pos); offs[pos] = (uint32_t)off; }
+    if (f0 || f1) {
+        double v0 = 0.0, v1 = 0.0;
+        if (pos < b.n) { if (f0) v0 = (double)__ldg(f0 + off); if (f1) v1 = (double)__ldg(f1 + off); }
+        if (f0) {
+            const double s = block_sum(v0, scratch), s2 = block_sum(v0 * v0, scratch);
+            if (threadIdx.x == 0) { atomicAdd(mom + 0, s); atomicAdd(mom + 1, s2); if (blockIdx.x == 0) atomicAdd(mom + 2, (double)b.n); }
+        }
+        if (f1) {
+            const double s = block_sum(v1, scratch), s2 = block_sum(v1 * v1, scratch);
+            if (threadIdx.x == 0) { atomicAdd(mom + 3, s); atomicAdd(mom + 4, s2); if (blockIdx.x == 0) atomicAdd(mom + 5, (double)b.n); }
+        }
+    }
 }
 
 // 0 = tensor cores where a kernel exists (64x64), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
@@ -568,8 +635,22 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)(m->hidden1 + m->hidden2) * 4, st));
     if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
     int n_partials = grid;
-    if (C::H1 == 64 && C::H2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32)) {
-        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs);
+    // batch-normalisation moments the caller did not supply are taken over this minibatch, in the gather pass where there is one
+    const float* mf0 = (hp.normalize_adv && !adv_mom) ? b.adv : nullptr;
+    const float* mf1 = (hp.normalize_ret && !ret_mom) ? b.ret : nullptr;
+    if (mf0 || mf1) GS_CUDA(cudaMemsetAsync(w.sq, 0, 6 * sizeof(double), st));
+    if (mf0) adv_mom = w.sq;
+    if (mf1) ret_mom = w.sq + 3;
+    const bool tensor_path = C::H1 == 64 && C::H2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
+    if (!tensor_path && (mf0 || mf1)) {
+        int64_t blocks = (b.n + 255) / 256;
+        const int cap = 4 * sm_count(device);
+        if (blocks > cap) blocks = cap;
+        if (mf0) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, mf0, w.sq); GS_LAUNCH_CHECK(); }
+        if (mf1) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, mf1, w.sq + 3); GS_LAUNCH_CHECK(); }
+    }
+    if (tensor_path) {
+        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, mf0, mf1, w.sq);
         GS_LAUNCH_CHECK();
         const int64_t tiles128 = (b.n + 127) / 128;
         const int sms = sm_count(device);
@@ -582,12 +663,10 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
         GS_LAUNCH_CHECK();
     }
     const int grid_used = n_partials;
-    if (C::kPersist) {
-        reduce_partials_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.grad_partials, grid_used, P, pstride, grads_flat);
-        GS_LAUNCH_CHECK();
-    }
-    finalize_metrics_kernel<<<1, 64, 0, st>>>(w.metric_partials, grid_used, ALGO, m->hidden1, m->hidden2, track ? 1 : 0, hp.vf_coef,
-                                              hp.ent_coef, hp.normalize_adv, hp.normalize_ret, w.dead, metrics);
+    reduce_and_finalize_kernel<<<(unsigned)((P + 255) / 256) + 1, 256, 0, st>>>(C::kPersist ? w.grad_partials : nullptr, grid_used, P, pstride,
+                                                                                  grads_flat, w.metric_partials, ALGO, m->hidden1, m->hidden2,
+                                                                                  track ? 1 : 0, hp.vf_coef, hp.ent_coef, hp.normalize_adv,
+                                                                                  hp.normalize_ret, w.dead, metrics);
     GS_LAUNCH_CHECK();
     return 0;
 }
@@ -663,7 +742,6 @@ int gs_ppo_step(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_ppo_hpara
                 float* grads_flat, double* metrics, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!mlp || !batch || !hp || !grads_flat || !metrics || !workspace) GS_FAIL("gs_ppo_step: NULL argument");
     if (!mlp->has_value) GS_FAIL("PPO requires a policy with a value head");  // agents/ppo/ppo_agent.py:41-44
-    if (hp->normalize_adv && !adv_moments) GS_FAIL("normalize_adv needs adv_moments");
     if (!batch->values_old || !batch->adv || !batch->ret || !batch->logp_old || !batch->actions || !batch->obs)
         GS_FAIL("gs_ppo_step: batch has NULL arrays");
     HpDev h;
@@ -679,8 +757,6 @@ int gs_reinforce_step(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_rei
                       const double* adv_moments, float* grads_flat, double* metrics, void* workspace, int64_t workspace_bytes,
                       void* stream) {
     if (!mlp || !batch || !hp || !grads_flat || !metrics || !workspace) GS_FAIL("gs_reinforce_step: NULL argument");
-    if (hp->normalize_adv && !adv_moments) GS_FAIL("normalize_adv needs adv_moments");
-    if (hp->normalize_returns && !ret_moments) GS_FAIL("normalize_returns needs ret_moments");
     if (hp->policy_targets != 0 && hp->policy_targets != 1) GS_FAIL("Invalid policy targets: %d", hp->policy_targets);
     if (!batch->adv || !batch->ret || !batch->logp_old || !batch->actions || !batch->obs) GS_FAIL("gs_reinforce_step: batch has NULL arrays");
     HpDev h;
@@ -696,6 +772,11 @@ int gs_clip_grad_norm(const gs_mlp_t* mlp, float* grads_flat, float max_norm, do
     if (!grads_flat || !metrics) GS_FAIL("gs_clip_grad_norm: NULL argument");
     const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
     cudaStream_t st = (cudaStream_t)stream;
+    if (po.total <= (1 << 17)) {          // every network of the registry: one block, one launch, no atomics
+        clip_grad_norm_kernel<<<1, 1024, 0, st>>>(grads_flat, po, max_norm, metrics);
+        GS_LAUNCH_CHECK();
+        return 0;
+    }
     double* sq = metrics + GS_M_SCRATCH;  // squared norms of [backbone, policy_head, value_head]
     GS_CUDA(cudaMemsetAsync(sq, 0, 3 * sizeof(double), st));
     const int blocks = (int)((po.total + 1023) / 1024 < 64 ? (po.total + 1023) / 1024 : 64);

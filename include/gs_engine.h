@@ -244,7 +244,9 @@ int gs_batch_moments(const gs_batch_t* batch, const float* field /* (T,N) */, do
 /* ---- PPOAgent.losses_for_batch fwd + bwd (agents/ppo/ppo_agent.py:21-152) ---------------------------
  * partials: workspace of gs_update_workspace_bytes(); grads_flat (P,) receives dLoss/dtheta (deterministic
  * two-stage reduction); metrics (double[GS_N_METRICS]) receives the finalised scalars of the metric enum.
- * adv_moments: device double[3] from gs_batch_moments when hp.normalize_adv == 1, else nullable. */
+ * adv_moments: device double[3] {sum, sum of squares, count} the "batch" advantage normalisation uses (gs_batch_moments,
+ * all-reduced over ranks by the caller when the minibatch is sharded); NULL with hp.normalize_adv == 1 = take them over
+ * this minibatch inside the call (fused into its gather pass). */
 /* Bytes of device scratch gs_ppo_step / gs_reinforce_step need for minibatches of up to max_batch samples (per-CTA partial
  * gradients and metrics + 4 bytes per sample for the translated sample offsets). */
 int64_t gs_update_workspace_bytes(const gs_mlp_t* mlp, int device, int64_t max_batch);

@@ -197,7 +197,7 @@ def flat_to_time_major(x_flat, T, Nn):
     return np.ascontiguousarray(x.reshape(Nn, T, *x.shape[1:]).swapaxes(0, 1))
 
 
-def update_step(algo, p_dev, batch, hp, *, activation="relu", max_norm=None):
+def update_step(algo, p_dev, batch, hp, *, activation="relu", max_norm=None, internal_moments=False):
     m = N.mlp_struct_from_params(p_dev, activation)
     P = N.lib().gs_mlp_param_count(C.byref(m))
     wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0, int(batch.n))
@@ -208,7 +208,12 @@ def update_step(algo, p_dev, batch, hp, *, activation="relu", max_norm=None):
     adv_mom = torch.zeros(3, dtype=torch.float64, device=DEV)
     ret_mom = torch.zeros(3, dtype=torch.float64, device=DEV)
     L = N.lib()
-    if algo == "ppo":
+    if internal_moments:                      # NULL moments: the step takes them over the minibatch itself
+        if algo == "ppo":
+            N.check(L.gs_ppo_step(C.byref(m), C.byref(batch), C.byref(hp), None, N.ptr(grads), N.ptr(metrics), N.ptr(ws), wsb, N.stream()))
+        else:
+            N.check(L.gs_reinforce_step(C.byref(m), C.byref(batch), C.byref(hp), None, None, N.ptr(grads), N.ptr(metrics), N.ptr(ws), wsb, N.stream()))
+    elif algo == "ppo":
         if hp.normalize_adv:
             N.check(L.gs_batch_moments(C.byref(batch), batch.adv, N.ptr(adv_mom), N.stream()))
         N.check(L.gs_ppo_step(C.byref(m), C.byref(batch), C.byref(hp), N.ptr(adv_mom), N.ptr(grads), N.ptr(metrics), N.ptr(ws), wsb, N.stream()))

@@ -366,3 +366,34 @@ def test_dead_units_are_counted_and_do_not_serialise_the_kernel(impl):
     np.testing.assert_allclose(m["opt/activations/backbone.0/dead_pct"], 1.0 / 64, atol=2e-4)
     np.testing.assert_allclose(m["opt/activations/backbone.2/dead_pct"], 1.0 / 64, atol=2e-4)
     assert dt < 0.05, f"update step took {dt * 1e3:.1f} ms with two dead units"
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("algo", ["ppo", "reinforce"])
+def test_step_takes_minibatch_moments_itself_when_none_are_given(algo, impl):
+    """NULL moments + a "batch" normalisation flag = moments of this minibatch, taken inside the call: same gradients and
+    metrics as gs_batch_moments followed by the step."""
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    n, D, A = 5000, 4, 2
+    g = torch.Generator().manual_seed(11)
+    p = P.random_params(D, (64, 64), A, seed=3, has_value=True)
+    obs = torch.randn(1, n, D, generator=g)
+    actions = torch.randint(0, A, (1, n), generator=g)
+    z = torch.randn(1, n, generator=g)
+    batch, keep = E.make_batch(1, n, E.cu(obs), E.cu(actions.int()), E.cu(z * 0.1 - 0.7), E.cu(z), E.cu(1.5 * z + 0.3), E.cu(2 * z - 1))
+    if algo == "ppo":
+        hp = _ppo_hp(N)
+    else:
+        hp = N.GsReinforceHparams()
+        hp.ent_coef, hp.policy_targets, hp.normalize_returns, hp.normalize_adv, hp.track_activations = 0.01, 0, 1, 1, 1
+    try:
+        N.check(N.lib().gs_set_update_impl(impl))
+        g_a, _, m_a = E.update_step(algo, E.dev_params(p), batch, hp)
+        g_b, _, m_b = E.update_step(algo, E.dev_params(p), batch, hp, internal_moments=True)
+    finally:
+        N.lib().gs_set_update_impl(0)
+    np.testing.assert_allclose(g_b, g_a, rtol=1e-6, atol=1e-9)
+    for k in m_a:
+        np.testing.assert_allclose(m_b[k], m_a[k], rtol=1e-6, atol=1e-9, err_msg=k)
