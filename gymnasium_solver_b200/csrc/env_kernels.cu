@@ -32,13 +32,27 @@ env_step_kernel(EnvDev h, const int32_t* __restrict__ actions, float* __restrict
     const int64_t i = (int64_t)blockIdx.x * kEnvThreads + threadIdx.x;
     if (i >= h.n) return;
     EnvRegs e;
-    env_load<KIND>(h, i, e);
+    // the reset-stream counter is only touched on the (rare) autoreset step: 8 B of the per-step HBM traffic saved
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e.s[k] = k < EnvDims<KIND>::S ? h.state[(int64_t)k * h.n + i] : 0.0;
+    e.ep_ret = h.ep_ret[i];
+    e.elapsed = h.elapsed[i];
+    e.ep_len = h.ep_len[i];
+    e.needs_reset = h.needs_reset[i];
+    const bool resetting = e.needs_reset != 0;
+    e.reset_count = resetting ? h.reset_count[i] : 0u;
     float o[EnvDims<KIND>::D];
     double r, ep_r;
     bool term, trunc;
     int ep_l;
     env_vec_step<KIND>(e, h.params, i, __ldg(actions + i), o, r, term, trunc, ep_r, ep_l);
-    env_store<KIND>(h, i, e);
+#pragma unroll
+    for (int k = 0; k < EnvDims<KIND>::S; ++k) h.state[(int64_t)k * h.n + i] = e.s[k];
+    h.ep_ret[i] = e.ep_ret;
+    h.elapsed[i] = e.elapsed;
+    h.ep_len[i] = e.ep_len;
+    if (resetting) h.reset_count[i] = e.reset_count;
+    h.needs_reset[i] = (uint8_t)e.needs_reset;
     if (EnvDims<KIND>::D == 4) {
         reinterpret_cast<float4*>(obs)[i] = make_float4(o[0], o[1], o[2], o[3]);
     } else if (EnvDims<KIND>::D == 2) {

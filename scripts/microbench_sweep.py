@@ -88,5 +88,32 @@ def main():
         del values, boot, rewards, u, dones, timeouts, adv, ret, obs, actions, logp, ws
 
 
+def env_sweep(reps=20):
+    """Unfused `gs_env_step` (state resident in HBM, episode-statistics outputs not requested): algorithmic bytes per env-step
+    from SURVEY 8(d); the kernel also carries the RecordEpisodeStatistics accumulators (ep_return fp64, ep_length) and the
+    autoreset flag, 26 B per env-step that the algorithmic figure does not count."""
+    dev = torch.device("cuda", 0)
+    L = N.lib()
+    hbm = 6557.1
+    print()
+    print("| env | n_envs | gs_env_step us | GB/s (algorithmic B/env-step) | of 6557 GB/s |")
+    print("|---|---|---|---|---|")
+    for env_id, bytes_per_step in (("CartPole-v1", 98), ("MountainCar-v0", 58), ("Acrobot-v1", 106)):
+        for n in (1 << 16, 1 << 20, 1 << 22):
+            h = C.c_void_p()
+            N.check(L.gs_env_create(N.ENV_KINDS[env_id], n, 0, 42, 0, 0, C.byref(h)))
+            D = L.gs_env_obs_dim(N.ENV_KINDS[env_id])
+            obs = torch.empty(n, D, device=dev)
+            rew = torch.empty(n, device=dev)
+            term, trunc = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+            acts = torch.randint(0, 2, (n,), device=dev, dtype=torch.int32)
+            st = N.stream()
+            N.check(L.gs_env_reset(h, N.ptr(obs), st))
+            t = timed(lambda: N.check(L.gs_env_step(h, N.ptr(acts), N.ptr(obs), N.ptr(rew), N.ptr(term), N.ptr(trunc), None, None, st)), reps)
+            print(f"| {env_id} | {n} | {t * 1e6:.1f} | {bytes_per_step * n / t / 1e9:.0f} ({bytes_per_step}) | {bytes_per_step * n / t / 1e9 / hbm:.2f} |")
+            L.gs_env_destroy(h)
+
+
 if __name__ == "__main__":
     main()
+    env_sweep()
