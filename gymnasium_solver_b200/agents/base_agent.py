@@ -223,6 +223,7 @@ class BaseAgent(nn.Module):
         b.values_old, b.adv, b.ret = N.ptr(tm["values"]), N.ptr(tm["adv"]), N.ptr(tm["ret"])
         b.n, b.idx, b.perm_key, b.perm_offset, b.perm_len = n, N.ptr(idx), perm_key, perm_offset, perm_len
         b.idx_map = N.ptr(idx_map)
+        b.packed = N.ptr(tm.get("packed"))
         return EngineBatch(b, (tm, idx, idx_map), n)
 
     def training_step(self, batch, batch_idx):
@@ -275,8 +276,23 @@ class BaseAgent(nn.Module):
                 for k in range(n_mb):
                     yield p, k, self._make_batch(tm, traj.T, traj.n_envs, n=B, perm_key=key, perm_offset=k * B, perm_len=total, idx_map=idx_map)
 
+    def _pack_rollout(self, traj: DeviceTrajectory) -> None:
+        """One 64-byte record per sample (gs_rollout_pack) so the tensor-core update kernel gathers a minibatch sample with a
+        single aligned access.  Only the 64x64 network has that kernel; the buffer is reused across rollouts."""
+        if tuple(getattr(self.config, "hidden_dims", ())) != (64, 64) or "packed" in traj.tm:
+            return
+        total = traj.T * traj.n_envs
+        buf = getattr(self, "_packed_records", None)
+        if buf is None or buf.numel() != total * 16:
+            buf = self._packed_records = torch.empty(total * 16, dtype=torch.float32, device=self.device)
+        full = self._make_batch(traj.tm, traj.T, traj.n_envs, n=total)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_rollout_pack(C.byref(full.struct), N.ptr(buf), N.stream()))
+        traj.tm["packed"] = buf
+
     def train_on_rollout(self, traj: DeviceTrajectory) -> None:
         self._early_stop_epoch = False
+        self._pack_rollout(traj)
         key = _mix64(int(self.config.seed) ^ (self.current_epoch * 0x100000001B3))
         for _, k, batch in self.minibatches(traj, key):
             self.training_step(batch, k)

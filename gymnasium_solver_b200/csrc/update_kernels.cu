@@ -474,6 +474,22 @@ __global__ void clip_scale_kernel(float* __restrict__ g, int64_t P, const double
     }
 }
 
+// ---- packed sample records: one 64-byte row per (t,n) so the minibatch gather is a single aligned access per sample ----------
+__global__ void rollout_pack_kernel(BatchDev b, float* __restrict__ packed) {
+    const int64_t total = (int64_t)b.T * b.N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float x[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) x[d] = d < b.D ? __ldcs(b.obs + i * b.D + d) : 0.f;
+        float4* dst = reinterpret_cast<float4*>(packed + i * GS_RECORD_FLOATS);
+        __stcs(dst + 0, make_float4(x[0], x[1], x[2], x[3]));
+        __stcs(dst + 1, make_float4(x[4], x[5], x[6], x[7]));
+        __stcs(dst + 2, make_float4(__int_as_float(__ldcs(b.actions + i)), __ldcs(b.logp_old + i), b.values_old ? __ldcs(b.values_old + i) : 0.f,
+                                    __ldcs(b.adv + i)));
+        __stcs(dst + 3, make_float4(__ldcs(b.ret + i), 0.f, 0.f, 0.f));
+    }
+}
+
 // grad norms + clip of a small parameter vector in ONE block: group sums of squares in a fixed order, then the scaling pass
 __global__ void __launch_bounds__(1024) clip_grad_norm_kernel(float* __restrict__ g, ParamOffsets po, float max_norm, double* __restrict__ metrics) {
     __shared__ double scratch[32];
@@ -698,6 +714,7 @@ static BatchDev to_dev(const gs_batch_t* b) {
     d.n = b->n; d.idx = b->idx; d.perm_key = b->perm_key; d.perm_offset = b->perm_offset; d.perm_len = b->perm_len;
     d.idx_map = b->idx_map; d.T = b->T; d.D = b->obs_dim; d.N = b->N; d.obs = b->obs; d.actions = b->actions;
     d.logp_old = b->logp_old; d.values_old = b->values_old; d.adv = b->adv; d.ret = b->ret;
+    d.packed = b->packed;
     return d;
 }
 
@@ -734,6 +751,22 @@ int gs_batch_moments(const gs_batch_t* batch, const float* field, double* out, v
     const int cap = 4 * sm_count(device);
     if (blocks > cap) blocks = cap;
     batch_moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, field, out);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream) {
+    if (!batch || !packed) GS_FAIL("gs_rollout_pack: NULL argument");
+    if (!batch->obs || !batch->actions || !batch->logp_old || !batch->adv || !batch->ret) GS_FAIL("gs_rollout_pack: batch has NULL arrays");
+    if (batch->T <= 0 || batch->N <= 0 || batch->obs_dim <= 0 || batch->obs_dim > 8) GS_FAIL("gs_rollout_pack: bad shape");
+    if (((uintptr_t)packed & 15) != 0) GS_FAIL("gs_rollout_pack: packed must be 16-byte aligned");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    const int64_t total = (int64_t)batch->T * batch->N;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = 16ll * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    rollout_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(to_dev(batch), packed);
     GS_LAUNCH_CHECK();
     return 0;
 }

@@ -26,6 +26,7 @@ struct BatchDev {
     const float* obs;
     const int32_t* actions;
     const float *logp_old, *values_old, *adv, *ret;
+    const float* packed;   // nullable: (T*N, 16) sample records (gs_rollout_pack)
 };
 
 struct HpDev {

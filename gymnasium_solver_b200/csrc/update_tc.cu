@@ -75,7 +75,8 @@ constexpr int oRed = oTmem + 16;        // PM_N doubles + 16 floats (block reduc
 constexpr int oStage = oRed + 320;      // gather staging [128 rows][16] fp32 (cp.async destination)
 static_assert(PM_N * 8 + 16 * 4 + 8 * 4 <= 320, "reduction scratch");
 constexpr int oScal1 = oStage + 128 * 64;   // second buffer of the 5 sample scalars [128 rows][5] (odd tiles; even tiles use slots 8..12 of the row)
-constexpr int kSmemBytes = oScal1 + 128 * 20;
+constexpr int oOffN = oScal1 + 128 * 20;    // translated offset of each row's sample in the tile after next [128] u32
+constexpr int kSmemBytes = oOffN + 128 * 4;
 static_assert(oTL % 1024 == 0 && oW2 % 1024 == 0 && oY % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM columns: A[b] = 128*b (hi +0, lo +64); acc[b] = 256 + 64*b; dW2|db2 (72 used of 80); tail accumulator; per-row scratch
@@ -414,6 +415,18 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     uint32_t pf_off = 0;                    // translated offset of the tile being prefetched
     float* sc1 = reinterpret_cast<float*>(smraw + tcu::oScal1) + row * 5 - 8;   // indexed like stg: scalars at [8..12]
     const uint32_t sc1_s = smem_u32(sc1);
+    uint32_t* offn = reinterpret_cast<uint32_t*>(smraw + tcu::oOffN) + row;
+    const bool packed = b.packed != nullptr;   // 64-byte sample records (gs_rollout_pack): the row is ONE aligned access
+    // packed gather: each of the row's four chunk threads copies its 16-byte quarter of the record; chunk 0 also the next offset
+    auto prefetch_record = [&](int64_t t_next) {
+        const int64_t p = t_next * tcu::kRows + row;
+        if (t_next < n_tiles && p < b.n) cp_async16(stg_s + 16 * chunk, b.packed + (int64_t)pf_off * GS_RECORD_FLOATS + 4 * chunk);
+        else { stg[4 * chunk] = 0.f; stg[4 * chunk + 1] = 0.f; stg[4 * chunk + 2] = 0.f; stg[4 * chunk + 3] = 0.f; }
+        if (chunk == 0) {
+            const int64_t p2 = (t_next + gridDim.x) * tcu::kRows + row;
+            if (t_next + gridDim.x < n_tiles && p2 < b.n) cp_async4(smem_u32(offn), offs + p2); else *offn = 0u;
+        }
+    };
     auto prefetch_stage = [&](int stage, int64_t t_next, uint32_t par = 0) {   // par: parity of the tile's position in this CTA's sequence
         float* sc = par ? sc1 : stg;
         const uint32_t sc_s = par ? sc1_s : stg_s;
@@ -435,7 +448,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 for (int d = 0; d < 8; ++d) stg[d] = 0.f;
             }
             const int64_t p2 = (t_next + gridDim.x) * tcu::kRows + row;
-            if (t_next + gridDim.x < n_tiles && p2 < b.n) cp_async4(stg_s + 52, offs + p2); else stg[13] = 0.f;
+            if (t_next + gridDim.x < n_tiles && p2 < b.n) cp_async4(smem_u32(offn), offs + p2); else *offn = 0u;
         } else if (stage == 1) {
             if (ok) { cp_async4(sc_s + 32, b.actions + off); cp_async4(sc_s + 36, b.logp_old + off); }
             else { sc[8] = 0.f; sc[9] = 0.f; }
@@ -449,9 +462,11 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     {
         const int64_t p0 = (int64_t)blockIdx.x * tcu::kRows + row;
         pf_off = p0 < b.n ? __ldg(offs + p0) : 0u;
+        if (packed) prefetch_record(blockIdx.x);
+        else {
 #pragma unroll
-#pragma unroll
-        for (int st = 0; st < 4; ++st) if (chunk == st) prefetch_stage(st, blockIdx.x, 0u);
+            for (int st = 0; st < 4; ++st) if (chunk == st) prefetch_stage(st, blockIdx.x, 0u);
+        }
     }
 
     float g[4] = {0.f, 0.f, 0.f, 0.f};      // d(loss)/d(head outputs) of the tile entering its backward phase
@@ -545,12 +560,16 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             float sx[16];                                            // the row's staging slot, read by its four chunk threads
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if ((D4 && q == 1) || q == 2) continue;              // the sample scalars (8..12) are read in F3
+                if ((D4 && q == 1) || q >= 2) continue;              // the sample scalars (8..12) are read in F3
                 const float4 v4 = *reinterpret_cast<const float4*>(stg + 4 * q);
                 sx[4 * q] = v4.x; sx[4 * q + 1] = v4.y; sx[4 * q + 2] = v4.z; sx[4 * q + 3] = v4.w;
             }
             if (D4) { sx[4] = sx[5] = sx[6] = sx[7] = 0.f; }
-            pf_off = __float_as_uint(sx[13]);                        // offset of the tile after u: its copies start after sync 2
+            pf_off = *offn;                                          // offset of the tile after u: its copies start after sync 2
+            if (packed && chunk == 0) {                              // the record slot is rewritten after sync 2: F3 reads the scalars from sc1
+#pragma unroll
+                for (int d = 8; d < 13; ++d) sc1[d] = stg[d];
+            }
             GS_TR(20);
 #pragma unroll
             for (int d = 0; d < 8; ++d) xk[d] = sx[d];
@@ -571,7 +590,10 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
         if (has_next && tid == 0) tcu::mbar_arrive(&bars[tcu::RDY_1]);   // -> fwd(u), dW2(t)
         fence_after_sync();
         GS_TR(7);
-        if (has_next && chunk == 0) prefetch_stage(0, tile_u + gridDim.x);   // every chunk thread has read the staging slots (sync 2)
+        if (has_next) {                                              // every chunk thread has read the staging slots (sync 2)
+            if (packed) prefetch_record(tile_u + gridDim.x);
+            else if (chunk == 0) prefetch_stage(0, tile_u + gridDim.x);
+        }
         // ---- dz1(t) = dh1 * act'(h1) -> dz1^T -> P, while fwd(u) runs ---------------------------------------------------------------
         if (has_cur) {
             float dz[16];
@@ -619,14 +641,14 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 }
             }
             tmem_st4(lane_addr + tcu::cOP + 4 * chunk, o4);
-            if (chunk == 1) prefetch_stage(1, tile_u + gridDim.x, cur);
+            if (chunk == 1 && !packed) prefetch_stage(1, tile_u + gridDim.x, cur);
         }
         GS_TR(10);
         tmem_st_wait();
         fence_before_sync();
         tcu::compute_sync();                                                                                    // sync 3
         fence_after_sync();
-        if (has_next && chunk == 2) prefetch_stage(2, tile_u + gridDim.x, cur);
+        if (has_next && chunk == 2 && !packed) prefetch_stage(2, tile_u + gridDim.x, cur);
         GS_TR(11);
         // ---- F3(u): loss and d(loss)/d(heads), redundantly by the four chunk threads of the row (metrics: the owner) -------------
 #pragma unroll
@@ -645,7 +667,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 float pl[PM_N];                                      // this sample's metric terms (non-owners: dead code)
 #pragma unroll
                 for (int i = 0; i < PM_N; ++i) pl[i] = 0.f;
-                const float* sc = nxt ? sc1 : stg;                   // tile u's scalars: buffer of its parity
+                const float* sc = (packed || nxt) ? sc1 : stg;       // tile u's scalars: buffer of its parity (packed: always the copy)
                 sample_loss<ALGO>(outv, A, __float_as_int(sc[8]), sc[9], sc[10], sc[11], sc[12], hp, ncs[0], ncs[1], ncs[2], ncs[3], ncs[4], g, pl);
 #pragma unroll
                 for (int i = 0; i < PM_N; ++i) pl_keep[i] = pl[i];
@@ -678,7 +700,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                 Yhi[idx] = gh; Ylo[idx] = g[r] - gh;
             }
         }
-        if (has_next && chunk == 3) prefetch_stage(3, tile_u + gridDim.x, cur);
+        if (has_next && chunk == 3 && !packed) prefetch_stage(3, tile_u + gridDim.x, cur);
         GS_TR(12);
         GS_TR(15);
         fence_proxy_async();

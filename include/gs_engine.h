@@ -143,7 +143,13 @@ typedef struct gs_batch {
     const float*   values_old; /* PPO only */
     const float*   adv;
     const float*   ret;
+    /* Optional (nullable): the same six arrays as ONE 64-byte record per (t,n) in time-major order, written by
+     * gs_rollout_pack once per rollout: {obs[0..7] (zero padded), action bits, logp_old, values_old, adv, ret, 0, 0, 0}.
+     * With it the minibatch gather of the tensor-core update kernel is one aligned 64-byte access per sample instead of
+     * seven scattered ones (one TLB lookup and two sectors instead of seven of each). */
+    const float*   packed;
 } gs_batch_t;
+#define GS_RECORD_FLOATS 16
 
 typedef struct gs_ppo_hparams {
     float clip_range;      /* agents/ppo/ppo_agent.py:59          */
@@ -250,6 +256,9 @@ int gs_batch_moments(const gs_batch_t* batch, const float* field /* (T,N) */, do
 /* Bytes of device scratch gs_ppo_step / gs_reinforce_step need for minibatches of up to max_batch samples (per-CTA partial
  * gradients and metrics + 4 bytes per sample for the translated sample offsets). */
 int64_t gs_update_workspace_bytes(const gs_mlp_t* mlp, int device, int64_t max_batch);
+/* Builds the packed sample records of a rollout (see gs_batch_t.packed) from batch->{obs,actions,logp_old,values_old,adv,ret}
+ * (values_old nullable: 0): packed is (T*N, GS_RECORD_FLOATS) floats, 16-byte aligned.  Streaming pass, once per rollout. */
+int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream);
 /* Kernel selection for gs_ppo_step / gs_reinforce_step: 0 (default) = tcgen05 tensor-core kernel where one exists (64x64
  * MLP: 3xTF32, fp32 TMEM accumulators), 1 = fp32 FMA-pipe kernel everywhere.  Env GS_UPDATE_IMPL=simt|tc sets the default. */
 int gs_set_update_impl(int impl);

@@ -191,6 +191,17 @@ def make_batch(T, Nn, obs_tm, actions_tm, logp_tm, values_tm, adv_tm, ret_tm, *,
     return b, keep
 
 
+def pack_rollout(batch, keep):
+    """gs_rollout_pack over the batch's arrays; sets batch.packed (and keeps the buffer alive)."""
+    total = int(batch.T) * int(batch.N)
+    buf = torch.full((total, 16), float("nan"), dtype=torch.float32, device=DEV)
+    N.check(N.lib().gs_rollout_pack(C.byref(batch), N.ptr(buf), N.stream()))
+    sync()
+    batch.packed = N.ptr(buf)
+    keep.append(buf)
+    return buf
+
+
 def flat_to_time_major(x_flat, T, Nn):
     """(N*T, ...) env-major -> (T, N, ...) time-major numpy."""
     x = np.asarray(x_flat)

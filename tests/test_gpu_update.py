@@ -397,3 +397,35 @@ def test_step_takes_minibatch_moments_itself_when_none_are_given(algo, impl):
     np.testing.assert_allclose(g_b, g_a, rtol=1e-6, atol=1e-9)
     for k in m_a:
         np.testing.assert_allclose(m_b[k], m_a[k], rtol=1e-6, atol=1e-9, err_msg=k)
+
+
+@pytest.mark.parametrize("D,A", [(4, 2), (6, 3), (2, 3)])
+def test_packed_sample_records_layout_and_identical_update(D, A):
+    """gs_rollout_pack writes {obs (zero padded to 8), action bits, logp_old, values_old, adv, ret, 0, 0, 0} per (t, n); the update
+    step that gathers from the records returns bit-identical gradients and metrics to the one that gathers the seven arrays."""
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    T, Nn = 9, 700
+    g = torch.Generator().manual_seed(21 + D)
+    p = P.random_params(D, (64, 64), A, seed=4, has_value=True)
+    obs = torch.randn(T, Nn, D, generator=g)
+    actions = torch.randint(0, A, (T, Nn), generator=g)
+    z = torch.randn(T, Nn, generator=g)
+    arrs = [obs, actions.int(), z * 0.1 - 0.7, z, 1.5 * z + 0.3, 2 * z - 1]
+    total = T * Nn
+    results = []
+    for use_packed in (False, True):
+        batch, keep = E.make_batch(T, Nn, *[E.cu(a) for a in arrs], n=4096, perm_key=5, perm_offset=1000, perm_len=total)
+        if use_packed:
+            rec = E.pack_rollout(batch, keep).cpu().numpy()
+            np.testing.assert_array_equal(rec[:, :D], obs.reshape(total, D).numpy())
+            assert (rec[:, D:8] == 0).all() and (rec[:, 13:] == 0).all()
+            np.testing.assert_array_equal(rec[:, 8].view(np.int32), actions.reshape(total).numpy().astype(np.int32))
+            for col, a in zip((9, 10, 11, 12), arrs[2:]):
+                np.testing.assert_array_equal(rec[:, col], a.reshape(total).numpy().astype(np.float32))
+        results.append(E.update_step("ppo", E.dev_params(p), batch, _ppo_hp(N), internal_moments=True))
+    (g0, _, m0), (g1, _, m1) = results
+    np.testing.assert_array_equal(g1, g0)
+    for k in m0:
+        np.testing.assert_array_equal(m1[k], m0[k], err_msg=k)
