@@ -108,27 +108,28 @@ __device__ __forceinline__ float ldg_stream(const float* p) { return __ldcs(p); 
 __device__ __forceinline__ uint8_t ldg_stream(const uint8_t* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float* p, float v) { __stcs(p, v); }
 
-// ---- pseudo-random bijection on [0, len): 4-round Feistel on an even number of bits + cycle walking.
+// ---- pseudo-random bijection on [0, len): 4-round alternating Feistel network on exactly ceil(log2(len)) bits + cycle walking.
 // Replaces the n_epochs*N*T Python index list of MultiPassRandomSampler (utils/samplers.py:29-34) with O(1) per sample.
+// The halves may differ by one bit (L: bits/2 high bits, R: the rest); round r XORs one half with a keyed hash of the other
+// (even rounds L ^= F(R), odd rounds R ^= F(L)), so every round is invertible whatever the widths.  A power-of-two length
+// (the usual rollout: N*T = 2^k) needs no cycle walking at all; otherwise fewer than half of the draws walk once more.
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
 __host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, uint64_t len, uint64_t key) {
     int bits = 2;
-    while ((1ull << bits) < len) bits += 2;
-    const int half = bits >> 1;
-    const uint32_t mask = (uint32_t)((1ull << half) - 1);
+    while ((1ull << bits) < len) bits += 1;
+    const int lb = bits >> 1, rb = bits - lb;
+    const uint32_t lmask = (uint32_t)((1ull << lb) - 1), rmask = (uint32_t)((1ull << rb) - 1);
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     do {
-        uint32_t L = (uint32_t)(x >> half) & mask, R = (uint32_t)x & mask;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t f = mix32(R ^ (k0 + 0x9E3779B9u * (uint32_t)r)) ^ mix32((R + k1) * 0x85EBCA6Bu + (uint32_t)r);
-            const uint32_t nL = R, nR = L ^ (f & mask);
-            L = nL; R = nR;
-        }
-        x = ((uint64_t)L << half) | R;
+        uint32_t L = (uint32_t)(x >> rb) & lmask, R = (uint32_t)x & rmask;
+        L ^= mix32(R * 0x9E3779B1u + k0) & lmask;
+        R ^= mix32(L * 0x85EBCA6Bu + k1) & rmask;
+        L ^= mix32(R * 0xC2B2AE35u + (k0 ^ 0x27D4EB2Fu)) & lmask;
+        R ^= mix32(L * 0x165667B1u + (k1 ^ 0x9E3779B9u)) & rmask;
+        x = ((uint64_t)L << rb) | R;
     } while (x >= len);
     return x;
 }

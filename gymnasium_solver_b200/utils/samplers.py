@@ -26,28 +26,28 @@ def _mix32(x: torch.Tensor) -> torch.Tensor:
 def feistel_permutation(length: int, key: int, device="cpu") -> torch.Tensor:
     """The bijection of [0, length) the update kernel evaluates per sample (int64 tensor perm[i] = pi_key(i)).
 
-    4-round Feistel network on an even number of bits covering ``length`` plus cycle walking; same arithmetic as
-    ``gs::feistel_permute`` in csrc/common.cuh (uint32 lanes emulated in int64).
+    4-round alternating Feistel network on exactly ceil(log2(length)) bits (halves may differ by one bit) plus cycle walking;
+    same arithmetic as ``gs::feistel_permute`` in csrc/common.cuh (uint32 lanes emulated in int64).  A power-of-two length
+    needs no cycle walking.
     """
     bits = 2
     while (1 << bits) < length:
-        bits += 2
-    half = bits >> 1
-    mask = (1 << half) - 1
+        bits += 1
+    lb = bits >> 1
+    rb = bits - lb
+    lmask, rmask = (1 << lb) - 1, (1 << rb) - 1
     k0, k1 = key & _M32, (key >> 32) & _M32
     x = torch.arange(length, dtype=torch.int64, device=device)
     pending = torch.ones(length, dtype=torch.bool, device=device)
-    first = True
     while bool(pending.any()):
         cur = x[pending]
-        L, R = (cur >> half) & mask, cur & mask
-        for r in range(4):
-            f = _mix32(R ^ ((k0 + 0x9E3779B9 * r) & _M32)) ^ _mix32((((R + k1) & _M32) * 0x85EBCA6B + r) & _M32)
-            L, R = R, L ^ (f & mask)
-        cur = (L << half) | R
-        x[pending] = cur
+        L, R = (cur >> rb) & lmask, cur & rmask
+        L = L ^ (_mix32((R * 0x9E3779B1 + k0) & _M32) & lmask)
+        R = R ^ (_mix32((L * 0x85EBCA6B + k1) & _M32) & rmask)
+        L = L ^ (_mix32((R * 0xC2B2AE35 + (k0 ^ 0x27D4EB2F)) & _M32) & lmask)
+        R = R ^ (_mix32((L * 0x165667B1 + (k1 ^ 0x9E3779B9)) & _M32) & rmask)
+        x[pending] = (L << rb) | R
         pending = x >= length
-        first = False
     return x
 
 

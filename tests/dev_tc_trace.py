@@ -19,6 +19,7 @@ actions = torch.randint(0, A, (T, Nn), generator=g)
 z = torch.randn(T, Nn, generator=g)
 dev = [E.cu(obs), E.cu(actions.int()), E.cu(z * 0.1 - 0.7), E.cu(z), E.cu(z + 0.3), E.cu(z * 2)]
 batch, keep = E.make_batch(T, Nn, *dev, n=1 << 20, perm_key=77, perm_offset=0, perm_len=T * Nn)
+E.pack_rollout(batch, keep)
 hp = N.GsPpoHparams(); hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef, hp.normalize_adv, hp.track_activations = 0.2, 0.2, 0.5, 0.01, 1, 1
 for _ in range(3):
     E.update_step("ppo", E.dev_params(p), batch, hp)

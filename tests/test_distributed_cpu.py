@@ -61,3 +61,30 @@ def test_gradient_average_and_global_moments_world2():
     for r in res:
         np.testing.assert_allclose(r[4], [allx.sum(), (allx ** 2).sum(), allx.size], rtol=1e-12)
         assert r[5] == 2.0
+
+
+def test_keyed_bijection_mirror_is_a_permutation_and_mixes():
+    """Host mirror of the in-kernel sample-id bijection (csrc/common.cuh::feistel_permute): a permutation for every length, a
+    different one per key, and without the structure a weak mixer would leave (order / neighbour correlation)."""
+    import torch
+    from gymnasium_solver_b200.utils.samplers import feistel_permutation
+
+    for length in (1, 2, 3, 5, 7, 96, 1000, 4096, 32769, 1 << 17):
+        perm = feistel_permutation(length, key=0xDEADBEEF12345678 & ((1 << 63) - 1))
+        assert perm.dtype == torch.int64 and perm.numel() == length
+        assert torch.equal(torch.sort(perm).values, torch.arange(length))
+    n = 1 << 16
+    a, b = feistel_permutation(n, key=1), feistel_permutation(n, key=2)
+    assert float((a == b).float().mean()) < 1e-3
+    x = torch.arange(n, dtype=torch.float64)
+    for p in (a, b):
+        pf = p.double()
+        corr = float(torch.corrcoef(torch.stack([x, pf]))[0, 1])
+        assert abs(corr) < 0.02, corr
+        d = (pf[1:] - pf[:-1]).abs()
+        assert 0.30 * n < float(d.mean()) < 0.37 * n           # neighbours land n/3 apart on average, like a random permutation
+        # every 1/8 slice of positions draws about 1/8 of its samples from every 1/8 slice of ids (minibatch = unbiased subset)
+        counts = torch.zeros(8, 8)
+        for k in range(8):
+            counts[k] = torch.bincount((p[k * n // 8:(k + 1) * n // 8] * 8 // n), minlength=8).float()
+        assert float((counts / (n / 64) - 1).abs().max()) < 0.15
