@@ -54,7 +54,7 @@ class GsBatch(C.Structure):
     _fields_ = [("n", C.c_int64), ("idx", C.c_void_p), ("perm_key", C.c_uint64), ("perm_offset", C.c_int64),
                 ("perm_len", C.c_int64), ("idx_map", C.c_void_p), ("T", C.c_int32), ("obs_dim", C.c_int32), ("N", C.c_int64),
                 ("obs", C.c_void_p), ("actions", C.c_void_p), ("logp_old", C.c_void_p), ("values_old", C.c_void_p),
-                ("adv", C.c_void_p), ("ret", C.c_void_p), ("packed", C.c_void_p)]
+                ("adv", C.c_void_p), ("ret", C.c_void_p), ("packed", C.c_void_p), ("prepared", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class GsPpoHparams(C.Structure):
@@ -98,6 +98,7 @@ SIGNATURES = {
     "gs_batch_moments": (_i32, [C.POINTER(GsBatch), _vp, _vp, _vp]),
     "gs_update_workspace_bytes": (_i64, [C.POINTER(GsMlp), _i32, _i64]),
     "gs_rollout_pack": (_i32, [C.POINTER(GsBatch), _vp, _vp]),
+    "gs_batch_prepare": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), _i32, _i32, _vp, _vp, _i64, _vp]),
     "gs_set_update_impl": (_i32, [_i32]),
     "gs_mlp_param_count": (_i64, [C.POINTER(GsMlp)]),
     "gs_ppo_step": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), C.POINTER(GsPpoHparams), _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -19,7 +19,7 @@ class PPOAgent(BaseAgent):
     def __init__(self, config, **kw):
         super().__init__(config, **kw)
         self.clip_range_vf = config.clip_range_vf
-        self._adv_mom = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._adv_mom = torch.zeros(6, dtype=torch.float64, device=self.device)   # {sum, sumsq, count} of adv (and of ret, unused)
 
     def losses_for_batch(self, batch, batch_idx):
         cfg = self.config
@@ -36,9 +36,12 @@ class PPOAgent(BaseAgent):
             st = N.stream()
             adv_mom = None                       # one rank: the step takes the minibatch moments itself, in its gather pass
             if hp.normalize_adv and self.world_size > 1:
-                self._adv_mom.zero_()
-                N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._adv_mom), st))
-                allreduce_moments(self._adv_mom, self.world_size)   # statistics of the GLOBAL minibatch (W-invariant update)
+                # sharded minibatch: gather pass + local moments, all-reduce them (statistics of the GLOBAL minibatch: the update is
+                # W-invariant), then the rest of the step on the offsets the gather pass left in the workspace
+                N.check(L.gs_batch_prepare(C.byref(mlp), C.byref(b.struct), 1, 0, N.ptr(self._adv_mom), N.ptr(self._workspace),
+                                           self._ws_bytes, st))
+                allreduce_moments(self._adv_mom, self.world_size)
+                b.struct.prepared = 1
                 adv_mom = self._adv_mom
             N.check(L.gs_ppo_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(adv_mom), N.ptr(model.flat_grads),
                                   N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))

@@ -17,7 +17,7 @@ from ..base_agent import BaseAgent, EngineLoss
 class REINFORCEAgent(BaseAgent):
     def __init__(self, config, **kw):
         super().__init__(config, **kw)
-        self._mom = torch.zeros(2, 3, dtype=torch.float64, device=self.device)
+        self._mom = torch.zeros(6, dtype=torch.float64, device=self.device)   # [0:3] adv, [3:6] ret: {sum, sumsq, count}
 
     def losses_for_batch(self, batch, batch_idx):
         cfg = self.config
@@ -37,13 +37,12 @@ class REINFORCEAgent(BaseAgent):
             st = N.stream()
             ret_mom = adv_mom = None             # one rank: the step takes the minibatch moments itself, in its gather pass
             if (hp.normalize_returns or hp.normalize_adv) and self.world_size > 1:
-                self._mom.zero_()
-                if hp.normalize_returns:
-                    N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.ret, N.ptr(self._mom[0]), st))
-                if hp.normalize_adv:
-                    N.check(L.gs_batch_moments(C.byref(b.struct), b.struct.adv, N.ptr(self._mom[1]), st))
+                # sharded minibatch: gather pass + local moments ([0:3] adv, [3:6] ret), all-reduce, then the rest of the step
+                N.check(L.gs_batch_prepare(C.byref(mlp), C.byref(b.struct), int(hp.normalize_adv), int(hp.normalize_returns),
+                                           N.ptr(self._mom), N.ptr(self._workspace), self._ws_bytes, st))
                 allreduce_moments(self._mom, self.world_size)
-                ret_mom, adv_mom = self._mom[0], self._mom[1]
+                b.struct.prepared = 1
+                adv_mom, ret_mom = self._mom[0:3], self._mom[3:6]
             N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(ret_mom), N.ptr(adv_mom),
                                         N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
         return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=False)

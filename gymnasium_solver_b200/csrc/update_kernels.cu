@@ -666,8 +666,10 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
         if (mf1) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, mf1, w.sq + 3); GS_LAUNCH_CHECK(); }
     }
     if (tensor_path) {
-        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, mf0, mf1, w.sq);
-        GS_LAUNCH_CHECK();
+        if (!b.prepared || mf0 || mf1) {
+            gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, mf0, mf1, w.sq);
+            GS_LAUNCH_CHECK();
+        }
         const int64_t tiles128 = (b.n + 127) / 128;
         const int sms = sm_count(device);
         n_partials = (int)(tiles128 < sms ? tiles128 : sms);
@@ -715,6 +717,7 @@ static BatchDev to_dev(const gs_batch_t* b) {
     d.idx_map = b->idx_map; d.T = b->T; d.D = b->obs_dim; d.N = b->N; d.obs = b->obs; d.actions = b->actions;
     d.logp_old = b->logp_old; d.values_old = b->values_old; d.adv = b->adv; d.ret = b->ret;
     d.packed = b->packed;
+    d.prepared = b->prepared;
     return d;
 }
 
@@ -768,6 +771,35 @@ int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream) {
     if (blocks > cap) blocks = cap;
     rollout_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(to_dev(batch), packed);
     GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv, int want_ret, double* moments, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    if (!mlp || !batch || !moments || !workspace) GS_FAIL("gs_batch_prepare: NULL argument");
+    if (validate_mlp(mlp)) return -1;
+    if (batch->n <= 0) GS_FAIL("empty minibatch");
+    if ((want_adv && !batch->adv) || (want_ret && !batch->ret)) GS_FAIL("gs_batch_prepare: batch has NULL arrays");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    if (workspace_bytes < ws_bytes(mlp, device, batch->n)) GS_FAIL("gs_batch_prepare: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const BatchDev b = to_dev(batch);
+    GS_CUDA(cudaMemsetAsync(moments, 0, 6 * sizeof(double), st));
+    const float* f0 = want_adv ? b.adv : nullptr;
+    const float* f1 = want_ret ? b.ret : nullptr;
+    const bool tensor_path = mlp->hidden1 == 64 && mlp->hidden2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
+    if (tensor_path) {
+        const UpdateWs w = carve(workspace, mlp, update_grid(device));
+        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, f0, f1, moments);
+        GS_LAUNCH_CHECK();
+    } else {
+        int64_t blocks = (b.n + 255) / 256;
+        const int cap = 4 * sm_count(device);
+        if (blocks > cap) blocks = cap;
+        if (f0) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, f0, moments); GS_LAUNCH_CHECK(); }
+        if (f1) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, f1, moments + 3); GS_LAUNCH_CHECK(); }
+    }
     return 0;
 }
 

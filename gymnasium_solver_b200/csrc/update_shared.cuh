@@ -27,6 +27,7 @@ struct BatchDev {
     const int32_t* actions;
     const float *logp_old, *values_old, *adv, *ret;
     const float* packed;   // nullable: (T*N, 16) sample records (gs_rollout_pack)
+    int prepared;          // gs_batch_prepare already wrote the sample offsets of this minibatch into the workspace
 };
 
 struct HpDev {

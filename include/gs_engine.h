@@ -148,6 +148,10 @@ typedef struct gs_batch {
      * With it the minibatch gather of the tensor-core update kernel is one aligned 64-byte access per sample instead of
      * seven scattered ones (one TLB lookup and two sectors instead of seven of each). */
     const float*   packed;
+    /* 1 = gs_batch_prepare already ran for exactly this minibatch on this workspace (sample offsets are in place): the
+     * step skips its gather pass.  Anything else about the batch must be unchanged between the two calls. */
+    int32_t prepared;
+    int32_t reserved_;
 } gs_batch_t;
 #define GS_RECORD_FLOATS 16
 
@@ -259,6 +263,12 @@ int64_t gs_update_workspace_bytes(const gs_mlp_t* mlp, int device, int64_t max_b
 /* Builds the packed sample records of a rollout (see gs_batch_t.packed) from batch->{obs,actions,logp_old,values_old,adv,ret}
  * (values_old nullable: 0): packed is (T*N, GS_RECORD_FLOATS) floats, 16-byte aligned.  Streaming pass, once per rollout. */
 int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream);
+/* First half of a step for callers that must exchange the minibatch moments between ranks before the update (sharded
+ * minibatches): runs the gather pass of gs_ppo_step / gs_reinforce_step (sample offsets into the workspace) and accumulates
+ * {sum, sumsq, count} of batch->adv into moments[0..2] (want_adv) and of batch->ret into moments[3..5] (want_ret); moments is
+ * zeroed by the call.  All-reduce moments, then call the step with them and batch->prepared = 1. */
+int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv, int want_ret, double* moments,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 /* Kernel selection for gs_ppo_step / gs_reinforce_step: 0 (default) = tcgen05 tensor-core kernel where one exists (64x64
  * MLP: 3xTF32, fp32 TMEM accumulators), 1 = fp32 FMA-pipe kernel everywhere.  Env GS_UPDATE_IMPL=simt|tc sets the default. */
 int gs_set_update_impl(int impl);

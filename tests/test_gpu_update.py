@@ -429,3 +429,51 @@ def test_packed_sample_records_layout_and_identical_update(D, A):
     np.testing.assert_array_equal(g1, g0)
     for k in m0:
         np.testing.assert_array_equal(m1[k], m0[k], err_msg=k)
+
+
+@pytest.mark.parametrize("algo", ["ppo", "reinforce"])
+def test_two_phase_step_for_sharded_minibatches_matches_the_one_call_step(algo):
+    """gs_batch_prepare (gather pass + local moments) -> [all-reduce by the caller] -> step with batch.prepared = 1 returns the
+    same bits as the single call that takes the moments itself."""
+    import ctypes as C
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    T, Nn, D, A = 16, 512, 4, 2
+    g = torch.Generator().manual_seed(33)
+    p = P.random_params(D, (64, 64), A, seed=6, has_value=True)
+    obs = torch.randn(T, Nn, D, generator=g)
+    actions = torch.randint(0, A, (T, Nn), generator=g)
+    z = torch.randn(T, Nn, generator=g)
+    arrs = [E.cu(a) for a in (obs, actions.int(), z * 0.1 - 0.7, z, 1.5 * z + 0.3, 2 * z - 1)]
+    batch, keep = E.make_batch(T, Nn, *arrs, n=3000, perm_key=9, perm_offset=2048, perm_len=T * Nn)
+    if algo == "ppo":
+        hp = _ppo_hp(N)
+    else:
+        hp = N.GsReinforceHparams()
+        hp.ent_coef, hp.policy_targets, hp.normalize_returns, hp.normalize_adv, hp.track_activations = 0.01, 0, 1, 1, 1
+    g_ref, _, m_ref = E.update_step(algo, E.dev_params(p), batch, hp, internal_moments=True)
+    # two-phase
+    pd = E.dev_params(p)
+    m = N.mlp_struct_from_params(pd, "relu")
+    L = N.lib()
+    Pn = L.gs_mlp_param_count(C.byref(m))
+    wsb = L.gs_update_workspace_bytes(C.byref(m), 0, int(batch.n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    grads = torch.empty(Pn, device="cuda")
+    met = torch.zeros(N.N_METRICS, dtype=torch.float64, device="cuda")
+    mom = torch.full((6,), float("nan"), dtype=torch.float64, device="cuda")
+    N.check(L.gs_batch_prepare(C.byref(m), C.byref(batch), 1, int(algo == "reinforce"), N.ptr(mom), N.ptr(ws), wsb, N.stream()))
+    batch.prepared = 1
+    if algo == "ppo":
+        N.check(L.gs_ppo_step(C.byref(m), C.byref(batch), C.byref(hp), N.ptr(mom), N.ptr(grads), N.ptr(met), N.ptr(ws), wsb, N.stream()))
+    else:
+        N.check(L.gs_reinforce_step(C.byref(m), C.byref(batch), C.byref(hp), N.ptr(mom[3:6]), N.ptr(mom[0:3]), N.ptr(grads), N.ptr(met),
+                                    N.ptr(ws), wsb, N.stream()))
+    torch.cuda.synchronize()
+    assert float(mom[2]) == batch.n
+    np.testing.assert_array_equal(grads.cpu().numpy(), g_ref)
+    mv = met.cpu().numpy()
+    for i, k in enumerate(N.METRIC_KEYS):
+        if not k.startswith("opt/grads"):
+            np.testing.assert_array_equal(mv[i], m_ref[k], err_msg=k)
