@@ -80,7 +80,7 @@ constexpr int kSmemBytes = oOffN + 128 * 4;
 static_assert(oTL % 1024 == 0 && oW2 % 1024 == 0 && oY % 1024 == 0, "swizzle atoms are 1024-byte aligned");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM columns: A[b] = 128*b (hi +0, lo +64); acc[b] = 256 + 64*b; dW2|db2 (72 used of 80); tail accumulator; per-row scratch
-constexpr uint32_t cA = 0, cAcc = 256, cW2 = 384, cC = 464, cOP = 480, kTmemCols = 512;
+constexpr uint32_t cA = 0, cAcc = 256, cW2 = 384, cC = 464, cOP = 480, cC2 = 496, kTmemCols = 512;   // cC2: hi*lo pass of the tail (second MMA warp)
 enum { BAR_FWD = 0, BAR_D, BAR_W, BAR_T, RDY_0, RDY_1, RDY_2 };   // MMA-complete barriers; operands-ready barriers
 // barrier among the 512 compute threads only (the MMA warp never joins it)
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -194,10 +194,12 @@ __device__ __forceinline__ void issue_dw2(uint32_t tmem_acc, uint32_t th, uint32
     }
 }
 // tail: A = [P ; S] (128 rows), B = Y (16 rows; lo copy 8 KB after hi)
-__device__ __forceinline__ void issue_tail(uint32_t tmem_acc, uint32_t th, uint32_t tl, uint32_t y, uint32_t accumulate) {
+// The three 3xTF32 passes are split over the two MMA warps (two accumulators, summed when they are flushed): passes
+// [p0, p1) go to tmem_acc.  hi*hi + lo*hi -> one warp, hi*lo -> the other: the group completes in ~2/3 of the time.
+__device__ __forceinline__ void issue_tail(uint32_t tmem_acc, uint32_t th, uint32_t tl, uint32_t y, uint32_t accumulate, int p0, int p1) {
     const uint32_t idesc = make_idesc_tf32(128, 16, 0, 0);
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
+    for (int pass = p0; pass < p1; ++pass) {
         const uint32_t a0 = pass == 1 ? tl : th, as = pass == 1 ? tcu::kLoSlab : tcu::kHiSlab;
         const uint32_t b0 = y + (pass == 2 ? 8192u : 0u);
 #pragma unroll
@@ -232,6 +234,13 @@ __device__ __forceinline__ void flush_wgrad(uint32_t lane_addr, int quad, int ch
     tmem_ld16(lane_addr + tcu::cW2 + 16 * chunk, v);
     float s16[16];
     if (chunk < 2) tmem_ld16(lane_addr + (chunk == 0 ? tcu::cC : tcu::cW2 + 64), s16);   // chunk 0: tail block; chunk 1: db2 in col 0
+    if (chunk == 0) {
+        float t16[16];
+        tmem_ld16(lane_addr + tcu::cC2, t16);                      // the tail's hi*lo pass has its own accumulator
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s16[i] += t16[i];
+    }
     tmem_ld_wait();
     auto put = [&](int64_t idx, float val) { out[idx] = first ? val : out[idx] + val; };
     if (owner) {
@@ -294,7 +303,7 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     if (warp == 0) tmem_alloc(tmem_slot, tcu::kTmemCols);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], i == tcu::BAR_T ? 2 : 1);   // the tail group is issued by both MMA warps
         fence_mbar_init();
     }
     {
@@ -373,11 +382,14 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
                     fence_after_sync();
                     if (elect_one()) { issue_ts_64x64(tmem, tcu::cA + 128u * nxt, sW2_, tcu::cAcc + 64u * nxt); mma_commit(&bars[tcu::BAR_FWD]); }  // fwd(u)
                 }
+                mbar_wait(&bars[tcu::RDY_2], nxt);                   // completion index it+1
+                fence_after_sync();
+                if (elect_one()) { issue_tail(tmem + tcu::cC2, sTH_, sTL_, sY_, acc_t, 2, 3); mma_commit(&bars[tcu::BAR_T]); }   // tail, hi*lo pass
             } else {
                 if (has_cur && elect_one()) { issue_dw2(tmem + tcu::cW2, sTH_, sTL_, acc_w); mma_commit(&bars[tcu::BAR_W]); }    // dW2 | db2 (t)
                 mbar_wait(&bars[tcu::RDY_2], nxt);                   // completion index it+1
                 fence_after_sync();
-                if (elect_one()) { issue_tail(tmem + tcu::cC, sTH_, sTL_, sY_, acc_t); mma_commit(&bars[tcu::BAR_T]); }          // dW1 | db1 | dWh
+                if (elect_one()) { issue_tail(tmem + tcu::cC, sTH_, sTL_, sY_, acc_t, 0, 2); mma_commit(&bars[tcu::BAR_T]); }    // dW1 | db1 | dWh
             }
         }
         return;
