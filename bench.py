@@ -111,8 +111,10 @@ def build_agent_for_bench(args, rank, world):
 def launches_per_step(cfg, world):
     """Engine kernels launched per training iteration (ours; torch's optimizer / bookkeeping kernels are not counted)."""
     n_mb = (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs)
-    per_rollout = 1 + 2 + 1 + 2          # collect, obs/reward moments, gae, adv/ret moments
-    per_mb = 1 + 1 + 1 + 1 + 2           # batch_moments, update, reduce_partials, finalize_metrics, grad_norm + clip_scale
+    tensor_path = tuple(cfg.hidden_dims) == (64, 64)
+    per_rollout = 1 + 2 + 1 + 2 + (1 if tensor_path else 0)   # collect, obs/reward moments, gae, adv/ret moments, rollout_pack
+    # gather pass (offsets + batch moments; gs_batch_prepare when sharded), update, reduce_and_finalize, clip_grad_norm
+    per_mb = (4 if tensor_path else 4 + 0)
     return per_rollout + n_mb * per_mb
 
 
@@ -206,7 +208,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/update), f64 (env physics)", "data": "synthetic",
             "config": {"workload": "CartPole-v1:ppo, 65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP (BASELINE.json configs[1])",
                        "n_envs_per_gpu": args.n_envs, "n_envs_total": args.n_envs * world, "n_steps": args.n_steps, "n_epochs": args.n_epochs,
-                       "batch_size_total": args.batch_size * world, "minibatches_per_step": launches_per_step(cfg, world) // 6,
+                       "batch_size_total": args.batch_size * world, "minibatches_per_step": (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs),
                        "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded, NCCL grad all-reduce per minibatch",
                        "l2": "rollout working set (>=300 MB per GPU) exceeds the 126 MB L2; no explicit flush",
                        "last_policy_loss": epoch_metrics.get("opt/loss/policy"), "last_ep_rew_mean": roll_metrics.get("roll/ep_rew/mean")},
@@ -250,6 +252,7 @@ def kernel_rooflines(agent, cfg, dev):
         return a.elapsed_time(b) / reps * 1e-3
 
     # fused update kernel (+ its two tiny reduction kernels): one minibatch per call, a different minibatch every call
+    agent._pack_rollout(traj)          # as train_on_rollout does: 64-byte sample records for the tensor-core kernel's gather
     batches = [b for _, _, b in agent.minibatches(traj, 12345)]
     it = [0]
 
