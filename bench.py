@@ -113,8 +113,9 @@ def launches_per_step(cfg, world):
     n_mb = (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs)
     tensor_path = tuple(cfg.hidden_dims) == (64, 64)
     per_rollout = 1 + 2 + 1 + 2 + (1 if tensor_path else 0)   # collect, obs/reward moments, gae, adv/ret moments, rollout_pack
-    # gather pass (offsets + batch moments; gs_batch_prepare when sharded), update, reduce_and_finalize, clip_grad_norm
-    per_mb = (4 if tensor_path else 4 + 0)
+    # tensor path: gather pass (offsets + batch moments; all of a rollout's up front when sharded), update kernel,
+    # gs_update_finish (reduction + NVLink gradient mean + metrics + clip + Adam).  FMA-pipe path: batch moments, update, finish.
+    per_mb = 3
     return per_rollout + n_mb * per_mb
 
 
@@ -209,7 +210,8 @@ def run_b200(args):
             "config": {"workload": "CartPole-v1:ppo, 65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP (BASELINE.json configs[1])",
                        "n_envs_per_gpu": args.n_envs, "n_envs_total": args.n_envs * world, "n_steps": args.n_steps, "n_epochs": args.n_epochs,
                        "batch_size_total": args.batch_size * world, "minibatches_per_step": (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs),
-                       "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded, NCCL grad all-reduce per minibatch",
+                       "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded; gradient mean per minibatch over NVLink peer memory inside gs_update_finish"
+                                      if agent._peer is not None else f"dp{world}: envs sharded" + ("; NCCL grad all-reduce per minibatch" if world > 1 else ""),
                        "l2": "rollout working set (>=300 MB per GPU) exceeds the 126 MB L2; no explicit flush",
                        "last_policy_loss": epoch_metrics.get("opt/loss/policy"), "last_ep_rew_mean": roll_metrics.get("roll/ep_rew/mean")},
             "clocks": clocks,

@@ -54,7 +54,8 @@ class GsBatch(C.Structure):
     _fields_ = [("n", C.c_int64), ("idx", C.c_void_p), ("perm_key", C.c_uint64), ("perm_offset", C.c_int64),
                 ("perm_len", C.c_int64), ("idx_map", C.c_void_p), ("T", C.c_int32), ("obs_dim", C.c_int32), ("N", C.c_int64),
                 ("obs", C.c_void_p), ("actions", C.c_void_p), ("logp_old", C.c_void_p), ("values_old", C.c_void_p),
-                ("adv", C.c_void_p), ("ret", C.c_void_p), ("packed", C.c_void_p), ("prepared", C.c_int32), ("reserved_", C.c_int32)]
+                ("adv", C.c_void_p), ("ret", C.c_void_p), ("packed", C.c_void_p), ("prepared", C.c_int32), ("defer_reduce", C.c_int32),
+                ("offsets", C.c_void_p)]
 
 
 class GsPpoHparams(C.Structure):
@@ -66,6 +67,19 @@ class GsReinforceHparams(C.Structure):
     _fields_ = [("ent_coef", C.c_float), ("policy_targets", C.c_int32), ("normalize_returns", C.c_int32),
                 ("normalize_adv", C.c_int32), ("track_activations", C.c_int32)]
 
+
+class GsAdam(C.Structure):
+    _fields_ = [("params_flat", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("step_count", C.c_void_p),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+class GsFinish(C.Structure):
+    _fields_ = [("algo", C.c_int32), ("track_activations", C.c_int32), ("normalize_adv", C.c_int32), ("normalize_ret", C.c_int32),
+                ("vf_coef", C.c_float), ("ent_coef", C.c_float), ("max_grad_norm", C.c_float), ("reserved_", C.c_int32)]
+
+
+PEER_HANDLE_BYTES = 64
+PEER_MAX_WORLD = 8
 
 # every symbol include/gs_engine.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
@@ -105,6 +119,10 @@ SIGNATURES = {
     "gs_reinforce_step": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), C.POINTER(GsReinforceHparams), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gs_clip_grad_norm": (_i32, [C.POINTER(GsMlp), _vp, _f32, _vp, _vp]),
     "gs_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _vp]),
+    "gs_peer_create": (_i32, [_i32, _i32, _i64, _i32, C.POINTER(_vp), _vp]),
+    "gs_peer_connect": (_i32, [_vp, _vp]),
+    "gs_peer_destroy": (_i32, [_vp]),
+    "gs_update_finish": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), C.POINTER(GsFinish), _vp, C.POINTER(GsAdam), _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

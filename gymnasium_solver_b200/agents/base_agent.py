@@ -7,13 +7,15 @@ agents/base_agent.py:253-366) — without PyTorch-Lightning: ``learn()`` drives 
 
 Engine mapping of one epoch:
   collect                       1 fused collect launch + 1 target kernel                     (RolloutCollector.collect)
-  for pass, minibatch           gs_batch_moments -> gs_ppo_step / gs_reinforce_step (forward + loss + backward, gradients
-                                written into the flat .grad buffer) -> [NCCL all-reduce] -> gs_clip_grad_norm ->
-                                torch optimizer.step()
+  for pass, minibatch           gs_ppo_step / gs_reinforce_step with defer_reduce (gather pass + forward + loss + backward, per-CTA
+                                partial gradients) -> gs_update_finish (ONE launch: ordered reduction, gradient exchange over
+                                NVLink peer memory, metrics, global-norm clip, Adam on the flat parameter vector)
+                                [generic path for overridden losses / other optimizers / KL early stop: gs_*_step ->
+                                 NCCL all-reduce -> gs_clip_grad_norm -> optimizer.step()]
 Metrics stay on device as a running sum and reach the host once per epoch.
 Data parallel: one process per GPU owns ``n_envs / world_size`` envs (global env ids keep RNG streams W-invariant); the
-only data-path collective is the gradient all-reduce per minibatch (+ one tiny all-reduce of the per-minibatch
-advantage moments per pass so "batch" normalisation means the GLOBAL minibatch).
+only data-path exchange is the gradient mean per minibatch (inside gs_update_finish) + ONE all-reduce per rollout of the
+minibatch advantage moments of all its minibatches, so "batch" normalisation means the GLOBAL minibatch.
 """
 from __future__ import annotations
 
@@ -29,9 +31,9 @@ import torch
 import torch.nn as nn
 
 from .. import _native as N
-from ..utils.distributed import average_gradients, shard_spec
+from ..utils.distributed import PeerGroup, allreduce_moments, average_gradients, shard_spec
 from ..utils.environment import build_env_from_config
-from ..utils.optimizer_factory import build_optimizer
+from ..utils.optimizer_factory import EngineAdam, build_optimizer
 from ..utils.policy_factory import build_policy_from_env_and_config
 from ..utils.rollout_collector import DeviceTrajectory, RolloutCollector
 from ..utils.rollout_buffer import RolloutTrajectory
@@ -52,6 +54,7 @@ class EngineBatch:
 
     def __init__(self, struct: N.GsBatch, keep, n: int):
         self.struct, self.keep, self.n = struct, keep, int(n)
+        self.moments = None          # device double[6] {adv, ret} x {sum, sumsq, count}, already reduced over ranks (prepared batch)
 
     def __len__(self):
         return self.n
@@ -148,6 +151,12 @@ class BaseAgent(nn.Module):
         self._metrics_sum = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
         self._metrics_n = 0
         self._moments = None
+        self._mom_scratch = torch.zeros(6, dtype=torch.float64, device=self.device)
+        # NVLink peer exchange for the gradient mean (gs_update_finish); "nccl" keeps torch.distributed on the generic path
+        self._peer = None
+        if self.world_size > 1 and bool(getattr(config, "fused_update", True)) and getattr(config, "grad_allreduce", "peer") == "peer":
+            P = int(self.policy_model.flat_params.numel())
+            self._peer = PeerGroup(self.rank, self.world_size, P, self.device)
 
     # ------------------------------------------------------------------------------------------------ construction
     def build_env(self, stage: str, **kwargs):
@@ -187,7 +196,8 @@ class BaseAgent(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ optimisation
     def configure_optimizers(self):
-        return build_optimizer(params=self.policy_model.parameters(), optimizer=self.config.optimizer, lr=self.policy_lr)
+        return build_optimizer(params=self.policy_model.parameters(), optimizer=self.config.optimizer, lr=self.policy_lr,
+                               model=self.policy_model)
 
     def optimizers(self):
         if self._optimizer is None:
@@ -226,9 +236,59 @@ class BaseAgent(nn.Module):
         b.packed = N.ptr(tm.get("packed"))
         return EngineBatch(b, (tm, idx, idx_map), n)
 
+    # ---- engine step: subclasses launch their kernel here ------------------------------------------------------------
+    def _step_moments(self):
+        """(want_adv, want_ret): which minibatch moments the step's "batch" normalisation needs."""
+        return 0, 0
+
+    def _launch_step(self, b: EngineBatch, *, defer: bool, moments=None) -> N.GsFinish:
+        raise NotImplementedError
+
+    def _prepare(self, b: EngineBatch, moments: torch.Tensor) -> None:
+        """Gather pass + local moments of a sharded minibatch (the caller all-reduces ``moments``)."""
+        want_adv, want_ret = self._step_moments()
+        mlp = N.mlp_struct(self.policy_model)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_batch_prepare(C.byref(mlp), C.byref(b.struct), want_adv, want_ret, N.ptr(moments), N.ptr(self._workspace),
+                                             self._ws_bytes, N.stream()))
+        b.struct.prepared = 1
+        b.moments = moments
+
+    def _global_moments(self, b: EngineBatch):
+        """Moments of the GLOBAL minibatch for a sharded step: those prepared up front, else prepare + all-reduce now."""
+        if self.world_size <= 1 or not any(self._step_moments()):
+            return None
+        if b.moments is None:
+            self._prepare(b, self._mom_scratch)
+            allreduce_moments(self._mom_scratch, self.world_size)
+        return b.moments
+
+    def _fused_step_ok(self, batch) -> bool:
+        own = getattr(type(self).losses_for_batch, "_engine_native", False)    # a user override takes the generic path
+        return (own and isinstance(batch, EngineBatch) and bool(getattr(self.config, "fused_update", True))
+                and getattr(self.config, "target_kl", None) is None and isinstance(self.optimizers(), EngineAdam)
+                and (self.world_size == 1 or self._peer is not None))
+
+    def _fused_training_step(self, b: EngineBatch) -> None:
+        """losses_for_batch + _backpropagate_and_step as two launches: the update kernel (per-CTA partials stay in the
+        workspace) and gs_update_finish (reduction, NVLink gradient mean, metrics, clip, Adam)."""
+        fin = self._launch_step(b, defer=True, moments=self._global_moments(b))
+        model, opt = self.policy_model, self.optimizers()
+        mlp, adam = N.mlp_struct(model), opt.adam_struct()
+        fin.max_grad_norm = float(self.config.max_grad_norm) if self.config.max_grad_norm is not None else 0.0
+        peer = self._peer.handle if self._peer is not None else None
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_update_finish(C.byref(mlp), C.byref(b.struct), C.byref(fin), N.ptr(model.flat_grads), C.byref(adam), peer,
+                                             N.ptr(self._metrics_dev), N.ptr(self._metrics_sum), N.ptr(self._workspace), self._ws_bytes,
+                                             N.stream()))
+        self._metrics_n += 1
+
     def training_step(self, batch, batch_idx):
         """reference agents/base_agent.py:330-366."""
         if self._early_stop_epoch:
+            return None
+        if self._fused_step_ok(batch):
+            self._fused_training_step(batch)
             return None
         result = self.losses_for_batch(batch, batch_idx)
         if result["early_stop_epoch"]:
@@ -290,11 +350,32 @@ class BaseAgent(nn.Module):
             N.check(N.lib().gs_rollout_pack(C.byref(full.struct), N.ptr(buf), N.stream()))
         traj.tm["packed"] = buf
 
+    def _prepare_all(self, batches) -> None:
+        """Sharded minibatches: run every gather pass of the rollout now and exchange ALL minibatch moments in ONE all-reduce
+        (instead of one per minibatch on the critical path of every step)."""
+        n, B = len(batches), self.local_batch_size
+        mom = getattr(self, "_mom_all", None)
+        if mom is None or mom.shape[0] != n:
+            mom = self._mom_all = torch.zeros(n, 6, dtype=torch.float64, device=self.device)
+        offs = None
+        if tuple(getattr(self.config, "hidden_dims", ())) == (64, 64):     # the tensor-core kernel reads translated offsets
+            offs = getattr(self, "_offs_all", None)
+            if offs is None or offs.shape != (n, B):
+                offs = self._offs_all = torch.empty(n, B, dtype=torch.int32, device=self.device)
+        for k, b in enumerate(batches):
+            if offs is not None:
+                b.struct.offsets = N.ptr(offs[k])
+            self._prepare(b, mom[k])
+        allreduce_moments(mom, self.world_size)
+
     def train_on_rollout(self, traj: DeviceTrajectory) -> None:
         self._early_stop_epoch = False
         self._pack_rollout(traj)
         key = _mix64(int(self.config.seed) ^ (self.current_epoch * 0x100000001B3))
-        for _, k, batch in self.minibatches(traj, key):
+        batches = [b for _, _, b in self.minibatches(traj, key)]
+        if self.world_size > 1 and any(self._step_moments()) and batches and self._fused_step_ok(batches[0]):
+            self._prepare_all(batches)
+        for k, batch in enumerate(batches):
             self.training_step(batch, k)
 
     def train_one_rollout(self) -> DeviceTrajectory:

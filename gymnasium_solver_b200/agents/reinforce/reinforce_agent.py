@@ -10,39 +10,40 @@ import ctypes as C
 import torch
 
 from ... import _native as N
-from ...utils.distributed import allreduce_moments
 from ..base_agent import BaseAgent, EngineLoss
 
 
 class REINFORCEAgent(BaseAgent):
-    def __init__(self, config, **kw):
-        super().__init__(config, **kw)
-        self._mom = torch.zeros(6, dtype=torch.float64, device=self.device)   # [0:3] adv, [3:6] ret: {sum, sumsq, count}
+    def _step_moments(self):
+        cfg = self.config
+        return int(getattr(cfg, "normalize_advantages", "off") == "batch"), int(cfg.normalize_returns == "batch")
 
-    def losses_for_batch(self, batch, batch_idx):
+    def _launch_step(self, b, *, defer: bool, moments=None) -> N.GsFinish:
         cfg = self.config
         if cfg.policy_targets not in ("returns", "advantages"):
             raise ValueError(f"Invalid policy targets: {cfg.policy_targets}")
-        b = self._as_engine_batch(batch)
         model = self.policy_model
         mlp = N.mlp_struct(model)
         hp = N.GsReinforceHparams()
         hp.ent_coef = float(self.ent_coef)
         hp.policy_targets = 0 if cfg.policy_targets == "returns" else 1
-        hp.normalize_returns = int(cfg.normalize_returns == "batch")
-        hp.normalize_adv = int(getattr(cfg, "normalize_advantages", "off") == "batch")
+        hp.normalize_adv, hp.normalize_returns = self._step_moments()
         hp.track_activations = int(bool(getattr(cfg, "track_activations", True)))
-        L = N.lib()
+        b.struct.defer_reduce = int(defer)
+        adv_mom = moments[0:3] if moments is not None else None     # [0:3] adv, [3:6] ret; None: the step's own gather pass
+        ret_mom = moments[3:6] if moments is not None else None
         with torch.cuda.device(self.device):
-            st = N.stream()
-            ret_mom = adv_mom = None             # one rank: the step takes the minibatch moments itself, in its gather pass
-            if (hp.normalize_returns or hp.normalize_adv) and self.world_size > 1:
-                # sharded minibatch: gather pass + local moments ([0:3] adv, [3:6] ret), all-reduce, then the rest of the step
-                N.check(L.gs_batch_prepare(C.byref(mlp), C.byref(b.struct), int(hp.normalize_adv), int(hp.normalize_returns),
-                                           N.ptr(self._mom), N.ptr(self._workspace), self._ws_bytes, st))
-                allreduce_moments(self._mom, self.world_size)
-                b.struct.prepared = 1
-                adv_mom, ret_mom = self._mom[0:3], self._mom[3:6]
-            N.check(L.gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(ret_mom), N.ptr(adv_mom),
-                                        N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes, st))
+            N.check(N.lib().gs_reinforce_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(ret_mom), N.ptr(adv_mom),
+                                              N.ptr(model.flat_grads), N.ptr(self._metrics_dev), N.ptr(self._workspace), self._ws_bytes,
+                                              N.stream()))
+        fin = N.GsFinish()
+        fin.algo, fin.track_activations, fin.normalize_adv, fin.normalize_ret = 1, hp.track_activations, hp.normalize_adv, hp.normalize_returns
+        fin.vf_coef, fin.ent_coef = 0.0, hp.ent_coef
+        return fin
+
+    def losses_for_batch(self, batch, batch_idx):
+        b = self._as_engine_batch(batch)
+        self._launch_step(b, defer=False, moments=self._global_moments(b))
         return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=False)
+
+    losses_for_batch._engine_native = True   # the fused step tail (BaseAgent._fused_training_step) may stand in for it

@@ -335,24 +335,41 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 __device__ __forceinline__ void finalize_metrics_body(const double* __restrict__ partials, int n_cta, int algo, int H1, int H2, int track,
                                                       float vf_coef, float ent_coef, int normalize_adv, int normalize_ret,
                                                       const uint32_t* __restrict__ dead, double* __restrict__ metrics) {
+    // needs blockDim.x >= 256.  Fixed summation order (8 strided groups per metric, then the groups in order): deterministic.
+    constexpr int kGroups = 8;
+    __shared__ double grp[PM_N * kGroups];
     __shared__ double tot[PM_N];
     __shared__ double dead_stats[4];
     const int tid = threadIdx.x;
-    if (tid < PM_N) {
+    if (tid < PM_N * kGroups) {
+        const int q = tid % PM_N, g = tid / PM_N;
         double s = 0.0;
-        for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * PM_N + tid];
-        tot[tid] = s;
+#pragma unroll 4
+        for (int c = g; c < n_cta; c += kGroups) s += __ldcg(partials + (size_t)c * PM_N + q);
+        grp[g * PM_N + q] = s;
     }
-    if (tid == 32 && track) {  // dead-neuron fractions per hooked layer: mean and max over neurons
-        for (int l = 0; l < 2; ++l) {
-            const int H = l == 0 ? H1 : H2, base = l == 0 ? 0 : H1;
-            double sum = 0.0, mx = 0.0;
-            for (int n = 0; n < H; ++n) { const double c = (double)dead[base + n]; sum += c; mx = c > mx ? c : mx; }
-            dead_stats[2 * l] = sum; dead_stats[2 * l + 1] = mx;
+    if (track && tid >= 192 && tid < 256) {   // dead-neuron fractions per hooked layer: mean and max over neurons (integer counts: order-free)
+        const int l = (tid - 192) >> 5, lane = tid & 31;
+        const int H = l == 0 ? H1 : H2, base = l == 0 ? 0 : H1;
+        unsigned long long sum = 0; uint32_t mx = 0;
+        for (int n = lane; n < H; n += 32) { const uint32_t c = __ldcg(dead + base + n); sum += c; mx = c > mx ? c : mx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const uint32_t m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = m2 > mx ? m2 : mx;
         }
+        if (lane == 0) { dead_stats[2 * l] = (double)sum; dead_stats[2 * l + 1] = (double)mx; }
     }
     __syncthreads();
-    if (tid != 0) return;
+    if (tid < PM_N) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) s += grp[g * PM_N + tid];
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;       // leaves this (inlined) function only: a caller with more work resumes with every thread
     const double B = tot[PM_COUNT];
     const double ent = tot[PM_ENT] / B;
     auto ustd = [](double s, double s2, double n) { double v = (s2 - s * s / n) / (n - 1.0); return sqrt(v > 0.0 ? v : 0.0); };
@@ -421,6 +438,158 @@ __global__ void reduce_and_finalize_kernel(const float* __restrict__ partials, i
     float s = 0.f;
     for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * pstride + i];
     grads[i] = s;
+}
+
+// ---- fused step tail (gs_update_finish): partial reduction -> NVLink gradient exchange -> metrics -> clip -> Adam ----------
+struct PeerDev {
+    int rank, world;
+    float* slots[GS_PEER_MAX_WORLD];      // slots[r]: rank r's receive buffer [2 phases][world][stride] (peer-mapped)
+    uint32_t* flags[GS_PEER_MAX_WORLD];   // flags[r]: rank r's arrival flags  [2 phases][world]
+    uint32_t epoch;                       // call counter (>= 1), identical on every rank
+    int64_t stride;
+};
+struct AdamDev { float *p, *m, *v; int64_t* step; float lr, beta1, beta2, eps; };
+struct FinishDev {
+    const float* partials; int n_cta; int64_t P, pstride;
+    const double* metric_partials; int n_metric_cta;
+    int algo, H1, H2, track, normalize_adv, normalize_ret; float vf_coef, ent_coef, max_norm;
+    const uint32_t* dead; uint32_t* ticket;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kFinishThreads = 1024;    // phase A: 64 parameters x 16 groups of partial vectors per block
+constexpr int kFinishGroups = kFinishThreads / 64;
+__global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad, PeerDev peer,
+                                                                       double* __restrict__ metrics, double* __restrict__ metrics_sum) {
+    __shared__ double scratch[32];
+    __shared__ double sq[3];
+    __shared__ float adam_c[2];
+    __shared__ int is_last;
+    const int tid = threadIdx.x;
+    const int phase = (int)(peer.epoch & 1u);
+    // ---- phase A (every block): sum of the per-CTA partial vectors in a fixed order (16 contiguous groups of CTAs, then the
+    //      groups in order); the result goes to grads (one rank) or straight into every rank's receive slot over NVLink
+    //      (posted P2P stores, no reads cross the link)
+    {
+        __shared__ float partg[kFinishGroups][64];
+        const int pl = tid & 63, cg = tid >> 6;
+        const int64_t i = (int64_t)blockIdx.x * 64 + pl;
+        float s = 0.f;
+        if (i < f.P && f.partials) {
+            const int per = (f.n_cta + kFinishGroups - 1) / kFinishGroups;
+            const int c0 = cg * per, c1 = min(f.n_cta, c0 + per);
+#pragma unroll 8
+            for (int c = c0; c < c1; ++c) s += __ldcg(f.partials + (size_t)c * f.pstride + i);
+        }
+        partg[cg][pl] = s;
+        __syncthreads();
+        if (cg == 0 && i < f.P) {
+            if (f.partials) {
+#pragma unroll
+                for (int g = 1; g < kFinishGroups; ++g) s += partg[g][pl];
+            } else {
+                s = grads[i];                                   // atomic-accumulation configurations
+            }
+            if (peer.world > 1) {
+                const int64_t o = ((int64_t)phase * peer.world + peer.rank) * peer.stride + i;
+                for (int r = 0; r < peer.world; ++r) peer.slots[r][o] = s;
+            } else {
+                grads[i] = s;
+            }
+        }
+    }
+    if (peer.world > 1) __threadfence_system(); else __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- phase B (the last block to arrive) -----------------------------------------------------------------------------------
+    if (peer.world > 1) {
+        __threadfence_system();
+        if (tid < peer.world) st_release_sys(peer.flags[tid] + phase * peer.world + peer.rank, peer.epoch);
+        if (tid < peer.world) {
+            const uint32_t* fl = peer.flags[peer.rank] + phase * peer.world + tid;
+            uint32_t spin = 0;
+            while (ld_acquire_sys(fl) != peer.epoch) {
+                if (++spin > (1u << 28)) __trap();              // a rank left the lock-step call sequence: fail, do not hang
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const float* mine = peer.slots[peer.rank] + (int64_t)phase * peer.world * peer.stride;
+        const float inv_w = 1.0f / (float)peer.world;
+        for (int64_t i = tid; i < f.P; i += kFinishThreads) {
+            float s = 0.f;
+            for (int r = 0; r < peer.world; ++r) s += __ldcg(mine + (int64_t)r * peer.stride + i);   // rank order: identical on every rank
+            grads[i] = s * inv_w;
+        }
+        __syncthreads();
+    }
+    // metric vector of the step (slots below GS_M_GRAD_NORM_ALL, batch count, return-normalisation slots)
+    finalize_metrics_body(f.metric_partials, f.n_metric_cta, f.algo, f.H1, f.H2, f.track, f.vf_coef, f.ent_coef, f.normalize_adv, f.normalize_ret,
+                          f.dead, metrics);
+    // group norms in a fixed order (utils/models.py:196-230), clip coefficient (torch.nn.utils.clip_grad_norm_)
+    double part[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = tid; i < po.total; i += kFinishThreads) {
+        const double v = (double)__ldcg(grads + i);            // other blocks wrote it in phase A: read through L2
+        const int grp = i < po.wp ? 0 : (i < po.wv ? 1 : 2);
+        part[grp] += v * v;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double t = block_sum(part[k], scratch);
+        if (tid == 0) sq[k] = t;
+    }
+    if (tid == 64 && ad.p) {
+        const int64_t step = *ad.step + 1;
+        const double bc1 = 1.0 - pow((double)ad.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)ad.beta2, (double)step);
+        adam_c[0] = (float)((double)ad.lr / bc1);
+        adam_c[1] = (float)sqrt(bc2);
+        *ad.step = step;
+    }
+    __syncthreads();
+    const double total = sqrt(sq[0] + sq[1] + sq[2]);
+    double coef = 1.0;
+    if (f.max_norm > 0.f) { coef = (double)f.max_norm / (total + 1e-6); coef = coef > 1.0 ? 1.0 : coef; }
+    if (tid == 0) {
+        metrics[GS_M_GRAD_NORM_ALL] = total;
+        metrics[GS_M_GRAD_NORM_BACKBONE] = sqrt(sq[0]);
+        metrics[GS_M_GRAD_NORM_POLICY] = sqrt(sq[1]);
+        metrics[GS_M_GRAD_NORM_VALUE] = sqrt(sq[2]);
+        metrics[GS_M_CLIP_COEF] = coef;
+        *f.ticket = 0u;
+    }
+    const float c = (float)coef;
+    const bool scale = coef < 1.0;
+    if (ad.p) {
+        const float step_size = adam_c[0], bc2_sqrt = adam_c[1];
+        float* __restrict__ pp = ad.p;
+        float* __restrict__ pm = ad.m;
+        float* __restrict__ pv = ad.v;
+#pragma unroll 4
+        for (int64_t i = tid; i < po.total; i += kFinishThreads) {
+            float gi = __ldcg(grads + i);
+            const float m0 = pm[i], v0 = pv[i], p0 = pp[i];
+            if (scale) { gi *= c; grads[i] = gi; }
+            const float mi = m0 + (gi - m0) * (1.f - ad.beta1);
+            const float vi = v0 * ad.beta2 + (1.f - ad.beta2) * gi * gi;
+            pm[i] = mi; pv[i] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + ad.eps;
+            pp[i] = p0 - step_size * (mi / denom);
+        }
+    } else if (scale) {
+        for (int64_t i = tid; i < po.total; i += kFinishThreads) grads[i] = __ldcg(grads + i) * c;
+    }
+    __syncthreads();
+    if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
 }
 
 // ---- minibatch moments of a rollout field (advantage / return batch normalisation) -------------------------------------
@@ -648,13 +817,14 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     const size_t smem = (size_t)C::kSmemFloats * sizeof(float);
     const int64_t pstride = (P + 3) & ~3ll;   // 16-byte aligned partial vectors
     const MlpDev md = to_dev(m);
-    if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)(m->hidden1 + m->hidden2) * 4, st));
     if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
     int n_partials = grid;
     // batch-normalisation moments the caller did not supply are taken over this minibatch, in the gather pass where there is one
     const float* mf0 = (hp.normalize_adv && !adv_mom) ? b.adv : nullptr;
     const float* mf1 = (hp.normalize_ret && !ret_mom) ? b.ret : nullptr;
-    if (mf0 || mf1) GS_CUDA(cudaMemsetAsync(w.sq, 0, 6 * sizeof(double), st));
+    // dead-unit counters and the moment scratch are adjacent in the workspace: one memset node covers both
+    // (+ the ticket counter of gs_update_finish behind the moments)
+    if (track || mf0 || mf1 || b.defer_reduce) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead) + 64, st));
     if (mf0) adv_mom = w.sq;
     if (mf1) ret_mom = w.sq + 3;
     const bool tensor_path = C::H1 == 64 && C::H2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
@@ -666,20 +836,22 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
         if (mf1) { batch_moments_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, mf1, w.sq + 3); GS_LAUNCH_CHECK(); }
     }
     if (tensor_path) {
+        uint32_t* offs = b.offsets ? b.offsets : w.offs;
         if (!b.prepared || mf0 || mf1) {
-            gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, mf0, mf1, w.sq);
+            gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, offs, mf0, mf1, w.sq);
             GS_LAUNCH_CHECK();
         }
         const int64_t tiles128 = (b.n + 127) / 128;
         const int sms = sm_count(device);
         n_partials = (int)(tiles128 < sms ? tiles128 : sms);
-        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, w.offs, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
+        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, offs, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
     } else {
         auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
         GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kThreads, smem, st>>>(md, b, hp, adv_mom, ret_mom, w.grad_partials, grads_flat, w.metric_partials, w.dead, pstride);
         GS_LAUNCH_CHECK();
     }
+    if (b.defer_reduce) return 0;             // gs_update_finish folds the partials (same n_partials: partials_for())
     const int grid_used = n_partials;
     reduce_and_finalize_kernel<<<(unsigned)((P + 255) / 256) + 1, 256, 0, st>>>(C::kPersist ? w.grad_partials : nullptr, grid_used, P, pstride,
                                                                                   grads_flat, w.metric_partials, ALGO, m->hidden1, m->hidden2,
@@ -718,6 +890,8 @@ static BatchDev to_dev(const gs_batch_t* b) {
     d.logp_old = b->logp_old; d.values_old = b->values_old; d.adv = b->adv; d.ret = b->ret;
     d.packed = b->packed;
     d.prepared = b->prepared;
+    d.defer_reduce = b->defer_reduce;
+    d.offsets = b->offsets;
     return d;
 }
 
@@ -791,7 +965,7 @@ int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv,
     const bool tensor_path = mlp->hidden1 == 64 && mlp->hidden2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
     if (tensor_path) {
         const UpdateWs w = carve(workspace, mlp, update_grid(device));
-        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, w.offs, f0, f1, moments);
+        gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, b.offsets ? b.offsets : w.offs, f0, f1, moments);
         GS_LAUNCH_CHECK();
     } else {
         int64_t blocks = (b.n + 255) / 256;
@@ -848,6 +1022,119 @@ int gs_clip_grad_norm(const gs_mlp_t* mlp, float* grads_flat, float max_norm, do
     grad_norm_kernel<<<blocks, 256, 0, st>>>(grads_flat, po, sq);
     GS_LAUNCH_CHECK();
     clip_scale_kernel<<<blocks, 256, 0, st>>>(grads_flat, po.total, sq, max_norm, metrics);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- NVLink peer group (CUDA IPC) --------------------------------------------------------------------------------------
+struct gs_peer {
+    int rank = 0, world = 1, device = 0;
+    int64_t stride = 0;                 // floats per slot (16-byte multiple)
+    void* base = nullptr;               // own allocation: [2][world][stride] floats, then [2][world] u32 flags
+    void* mapped[GS_PEER_MAX_WORLD] = {};   // peers' allocations (own rank: base)
+    bool connected = false;
+    uint32_t epoch = 0;
+};
+static size_t peer_slot_bytes(const gs_peer* p) { return ((size_t)2 * p->world * p->stride * 4 + 255) / 256 * 256; }
+
+int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_peer_t** out, void* handle_out_host) {
+    if (!out || !handle_out_host) GS_FAIL("gs_peer_create: NULL argument");
+    if (world_size < 2 || world_size > GS_PEER_MAX_WORLD) GS_FAIL("gs_peer_create: world_size %d outside 2..%d", world_size, GS_PEER_MAX_WORLD);
+    if (rank < 0 || rank >= world_size) GS_FAIL("gs_peer_create: bad rank %d/%d", rank, world_size);
+    if (max_floats <= 0) GS_FAIL("gs_peer_create: max_floats must be positive");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GS_PEER_HANDLE_BYTES, "IPC handle size");
+    GS_CUDA(cudaSetDevice(device));
+    gs_peer* p = new gs_peer();
+    p->rank = rank; p->world = world_size; p->device = device;
+    p->stride = (max_floats + 3) & ~3ll;
+    const size_t bytes = peer_slot_bytes(p) + 256;
+    if (cudaMalloc(&p->base, bytes) != cudaSuccess) { delete p; GS_FAIL("gs_peer_create: cudaMalloc of %zu bytes failed", bytes); }
+    cudaMemset(p->base, 0, bytes);
+    cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p->base);
+    if (e != cudaSuccess) { cudaFree(p->base); delete p; GS_FAIL("gs_peer_create: cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out_host, &h, sizeof(h));
+    *out = p;
+    return 0;
+}
+
+int gs_peer_connect(gs_peer_t* p, const void* all_handles_host) {
+    if (!p || !all_handles_host) GS_FAIL("gs_peer_connect: NULL argument");
+    if (p->connected) GS_FAIL("gs_peer_connect: already connected");
+    GS_CUDA(cudaSetDevice(p->device));
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) { p->mapped[r] = p->base; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles_host + (size_t)r * GS_PEER_HANDLE_BYTES, sizeof(h));
+        const cudaError_t e = cudaIpcOpenMemHandle(&p->mapped[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != p->rank && p->mapped[q]) { cudaIpcCloseMemHandle(p->mapped[q]); p->mapped[q] = nullptr; }
+            GS_FAIL("gs_peer_connect: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+    }
+    p->connected = true;
+    return 0;
+}
+
+int gs_peer_destroy(gs_peer_t* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; ++r) if (r != p->rank && p->mapped[r]) cudaIpcCloseMemHandle(p->mapped[r]);
+    if (p->base) cudaFree(p->base);
+    delete p;
+    return 0;
+}
+
+int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_finish_t* fin, float* grads_flat, const gs_adam_t* adam, gs_peer_t* peer,
+                     double* metrics, double* metrics_sum, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!mlp || !batch || !fin || !grads_flat || !metrics || !workspace) GS_FAIL("gs_update_finish: NULL argument");
+    if (validate_mlp(mlp)) return -1;
+    if (batch->n <= 0) GS_FAIL("gs_update_finish: batch must be the deferred step's minibatch");
+    if (fin->algo != ALGO_PPO && fin->algo != ALGO_REINFORCE) GS_FAIL("gs_update_finish: bad algo %d", fin->algo);
+    if (adam && (!adam->params_flat || !adam->exp_avg || !adam->exp_avg_sq || !adam->step_count)) GS_FAIL("gs_update_finish: adam has NULL pointers");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    if (workspace_bytes < ws_bytes(mlp, device, 0)) GS_FAIL("gs_update_finish: workspace too small");
+    const int64_t P = mlp_param_count(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
+    const UpdateWs w = carve(workspace, mlp, update_grid(device));
+    FinishDev f;
+    // the partial vectors the deferred step left behind (mirrors launch_update_cfg)
+    const bool persist = mlp->hidden1 <= 64 && mlp->hidden2 <= 64;
+    const int S = (mlp->hidden1 <= 64) ? 128 : 64;
+    const int64_t n_tiles = (batch->n + S - 1) / S;
+    const int grid_max = update_grid(device);
+    int n_cta = (int)(n_tiles < grid_max ? n_tiles : grid_max);
+    const bool tensor_path = mlp->hidden1 == 64 && mlp->hidden2 == 64 && update_impl() == 0 && (int64_t)batch->T * batch->N < (1ll << 32);
+    if (tensor_path) { const int sms = sm_count(device); n_cta = (int)(n_tiles < sms ? n_tiles : sms); }
+    f.partials = persist ? w.grad_partials : nullptr;
+    f.n_cta = n_cta; f.n_metric_cta = n_cta;
+    f.P = P; f.pstride = (P + 3) & ~3ll;
+    f.metric_partials = w.metric_partials;
+    f.algo = fin->algo; f.H1 = mlp->hidden1; f.H2 = mlp->hidden2; f.track = fin->track_activations ? 1 : 0;
+    f.normalize_adv = fin->normalize_adv; f.normalize_ret = fin->normalize_ret;
+    f.vf_coef = fin->vf_coef; f.ent_coef = fin->ent_coef; f.max_norm = fin->max_grad_norm;
+    f.dead = w.dead; f.ticket = (uint32_t*)((char*)w.sq + 56);
+    AdamDev ad = {};
+    if (adam) { ad.p = adam->params_flat; ad.m = adam->exp_avg; ad.v = adam->exp_avg_sq; ad.step = adam->step_count;
+                ad.lr = adam->lr; ad.beta1 = adam->beta1; ad.beta2 = adam->beta2; ad.eps = adam->eps; }
+    PeerDev pd = {};
+    pd.world = 1;
+    if (peer) {
+        if (!peer->connected) GS_FAIL("gs_update_finish: peer group is not connected (gs_peer_connect)");
+        if (peer->device != device) GS_FAIL("gs_update_finish: peer group belongs to device %d, current device is %d", peer->device, device);
+        if (f.pstride > peer->stride) GS_FAIL("gs_update_finish: peer slots hold %lld floats, the model has %lld", (long long)peer->stride, (long long)P);
+        pd.rank = peer->rank; pd.world = peer->world; pd.stride = peer->stride;
+        pd.epoch = ++peer->epoch;
+        for (int r = 0; r < peer->world; ++r) {
+            pd.slots[r] = (float*)peer->mapped[r];
+            pd.flags[r] = (uint32_t*)((char*)peer->mapped[r] + peer_slot_bytes(peer));
+        }
+    }
+    const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
+    const unsigned blocks = (unsigned)((P + 63) / 64);
+    update_finish_kernel<<<blocks, kFinishThreads, 0, (cudaStream_t)stream>>>(f, po, grads_flat, ad, pd, metrics, metrics_sum);
     GS_LAUNCH_CHECK();
     return 0;
 }

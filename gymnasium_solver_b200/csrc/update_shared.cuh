@@ -28,6 +28,8 @@ struct BatchDev {
     const float *logp_old, *values_old, *adv, *ret;
     const float* packed;   // nullable: (T*N, 16) sample records (gs_rollout_pack)
     int prepared;          // gs_batch_prepare already wrote the sample offsets of this minibatch into the workspace
+    int defer_reduce;      // leave the per-CTA partials in the workspace: gs_update_finish completes the step
+    uint32_t* offsets;     // nullable: caller-owned offsets buffer (instead of the workspace's)
 };
 
 struct HpDev {

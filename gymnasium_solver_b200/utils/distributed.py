@@ -7,7 +7,11 @@ The reference has no distributed code; this is the engine's own l
     per minibatch, before the global-norm clip — every rank then takes the identical optimizer step, so weights stay
     bit-identical without broadcasts;
   * ``allreduce_moments`` makes "batch" advantage normalisation use the GLOBAL minibatch statistics.
-Works with the NCCL backend on GPUs and with gloo on CPU tensors (tests)."""
+Works with the NCCL backend on GPUs and with gloo on CPU tensors (tests).
+
+``PeerGroup`` is the NVLink exchange the fused step tail (``gs_update_finish``) uses instead of NCCL for the gradient: one
+IPC-shared device buffer of receive slots + flags per rank; the kernel stores its gradient into every rank's slot, signals,
+waits, and sums the slots in rank order.  torch.distributed only carries the 64-byte IPC handles at start-up."""
 from __future__ import annotations
 
 import os
@@ -39,6 +43,50 @@ def shard_spec(n_envs_total: int, batch_size_total: int, rank: int, world_size: 
 
 def env_rank_world():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+class PeerGroup:
+    """gs_peer_t of this rank, connected to every other rank of the default process group (one node, <= 8 GPUs)."""
+
+    def __init__(self, rank: int, world_size: int, max_floats: int, device: torch.device, group=None):
+        import ctypes as C
+
+        from .. import _native as N
+
+        if not (2 <= world_size <= N.PEER_MAX_WORLD):
+            raise N.EngineError(f"peer exchange supports 2..{N.PEER_MAX_WORLD} ranks, got {world_size}")
+        self._N, self.handle = N, C.c_void_p()
+        mine = (C.c_ubyte * N.PEER_HANDLE_BYTES)()
+        N.check(N.lib().gs_peer_create(rank, world_size, int(max_floats), int(device.index), C.byref(self.handle), mine))
+        try:
+            gathered = exchange_handles(bytes(mine), world_size, device, group)
+            N.check(N.lib().gs_peer_connect(self.handle, gathered))
+        except Exception:
+            self.close()
+            raise
+        if dist.is_initialized():
+            dist.barrier(group=group)        # nobody signals before every rank has mapped every buffer
+
+    def close(self) -> None:
+        if self.handle:
+            self._N.lib().gs_peer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def exchange_handles(mine: bytes, world_size: int, device, group=None) -> bytes:
+    """all_gather of one fixed-size opaque handle per rank, concatenated in rank order (any backend)."""
+    backend = dist.get_backend(group)
+    dev = device if backend == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(t) for _ in range(world_size)]
+    dist.all_gather(out, t, group=group)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
 
 
 def average_gradients(flat_grads: torch.Tensor, world_size: int, group=None) -> torch.Tensor:

@@ -151,7 +151,13 @@ typedef struct gs_batch {
     /* 1 = gs_batch_prepare already ran for exactly this minibatch on this workspace (sample offsets are in place): the
      * step skips its gather pass.  Anything else about the batch must be unchanged between the two calls. */
     int32_t prepared;
-    int32_t reserved_;
+    /* 1 = stop after the update kernel: the per-CTA partial gradients / metric partials stay in the workspace and
+     * gs_update_finish completes the step (ordered reduction, gradient all-reduce, metrics, clip, Adam) in one launch. */
+    int32_t defer_reduce;
+    /* Optional (nullable) caller-owned buffer of n uint32 time-major sample offsets.  gs_batch_prepare writes it, a step
+     * with prepared = 1 reads it; NULL = the workspace's own buffer (one minibatch at a time).  Lets a caller prepare every
+     * minibatch of a rollout up front and exchange all their moments between ranks in ONE collective. */
+    uint32_t* offsets;
 } gs_batch_t;
 #define GS_RECORD_FLOATS 16
 
@@ -287,6 +293,50 @@ int gs_clip_grad_norm(const gs_mlp_t* mlp, float* grads_flat, float max_norm, do
  * default host path keeps torch.optim, this is the graph-capturable variant. step_count: device int64[1]. */
 int gs_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, int64_t n,
                  int64_t* step_count, float lr, float beta1, float beta2, float eps, void* stream);
+
+/* ---- fused step tail: BaseAgent._backpropagate_and_step (agents/base_agent.py:591-621) in ONE launch -----------------
+ * After a step called with batch->defer_reduce = 1, gs_update_finish
+ *   1. sums the per-CTA partial gradient vectors in CTA order (deterministic),
+ *   2. with a peer group: writes the local gradient into every rank's receive slot over NVLink (P2P stores), signals,
+ *      waits for the other ranks' signals and sums the slots in rank order, divided by world_size (every rank computes the
+ *      bit-identical mean: weights stay identical without a broadcast) -- the gradient all-reduce of SURVEY.md 8(e),
+ *   3. finalises the metric vector (as gs_ppo_step / gs_reinforce_step do) and adds it into metrics_sum (nullable),
+ *   4. takes the group norms (utils/models.py:196-230), applies the global-norm clip (agents/base_agent.py:604-617),
+ *      leaves the clipped mean gradient in grads_flat,
+ *   5. applies torch.optim.Adam's update (utils/optimizer_factory.py:6-29) when adam != NULL and bumps *adam->step_count.
+ * Every rank of a peer group must make the same sequence of gs_update_finish calls. */
+typedef struct gs_adam {
+    float*   params_flat;
+    float*   exp_avg;
+    float*   exp_avg_sq;
+    int64_t* step_count; /* device int64[1]: steps taken so far */
+    float lr, beta1, beta2, eps;
+} gs_adam_t;
+
+typedef struct gs_finish {
+    int32_t algo;              /* 0 = PPO, 1 = REINFORCE (which metric slots the deferred step fills)        */
+    int32_t track_activations; /* as passed to the deferred step                                             */
+    int32_t normalize_adv;
+    int32_t normalize_ret;
+    float   vf_coef;
+    float   ent_coef;
+    float   max_grad_norm;     /* <= 0: no clip (norms are still reported)                                   */
+    int32_t reserved_;
+} gs_finish_t;
+
+/* NVLink peer group for the gradient exchange: every rank allocates one device buffer of receive slots + flags
+ * (gs_peer_create), the 64-byte CUDA IPC handles are exchanged by the caller (any host channel, e.g. an all_gather over
+ * the torch.distributed store), gs_peer_connect maps the other ranks' buffers.  world_size <= 8 (one NVSwitch domain). */
+typedef struct gs_peer gs_peer_t;
+#define GS_PEER_HANDLE_BYTES 64
+#define GS_PEER_MAX_WORLD 8
+int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_peer_t** out, void* handle_out_host);
+int gs_peer_connect(gs_peer_t* peer, const void* all_handles_host /* world_size * GS_PEER_HANDLE_BYTES, rank order */);
+int gs_peer_destroy(gs_peer_t* peer);
+int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch /* the deferred step's minibatch */, const gs_finish_t* fin,
+                     float* grads_flat, const gs_adam_t* adam /* nullable: no optimizer step */,
+                     gs_peer_t* peer /* nullable: single rank */, double* metrics, double* metrics_sum /* nullable */,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

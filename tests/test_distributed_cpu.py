@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gymnasium_solver_b200.utils.distributed import allreduce_moments, average_gradients, max_over_ranks, shard_spec
+from gymnasium_solver_b200.utils.distributed import allreduce_moments, average_gradients, exchange_handles, max_over_ranks, shard_spec
 
 
 def test_shard_spec_partitions_envs_and_batches():
@@ -37,6 +37,9 @@ def _worker(rank, world, port, out):
         mom = torch.tensor([x.sum(), (x * x).sum(), float(x.numel())], dtype=torch.float64)
         allreduce_moments(mom, world)
         t = max_over_ranks(1.0 + rank, torch.device("cpu"), world)
+        # the 64-byte IPC handles of the NVLink peer group travel through the same process group, concatenated in rank order
+        handles = exchange_handles(bytes([rank + 1]) * 64, world, torch.device("cpu"))
+        assert handles == b"".join(bytes([r + 1]) * 64 for r in range(world))
         out.put((rank, local.numpy(), grads.numpy(), x.numpy(), mom.numpy(), t))
     finally:
         dist.destroy_process_group()

@@ -204,3 +204,77 @@ def test_checkpoint_roundtrip(tmp_path):
     assert b.get_rollout_collector("train").total_steps == 256
     assert set(torch.load(tmp_path / "ck" / "model.pt").keys()) == {"backbone.0.weight", "backbone.0.bias", "backbone.2.weight", "backbone.2.bias",
                                                                    "policy_head.weight", "policy_head.bias", "value_head.weight", "value_head.bias"}
+
+
+@pytest.mark.parametrize("algo,model_id", [("ppo", "mlp_64x64"), ("ppo", "mlp_small"), ("reinforce", "mlp_64x64")])
+def test_fused_step_tail_matches_the_generic_path(algo, model_id):
+    """gs_update_finish (ordered reduction + metrics + clip + Adam in one launch) against the unfused sequence
+    gs_*_step -> gs_clip_grad_norm -> torch.optim.Adam.step() on the same rollout, same minibatches."""
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.optimizer_factory import EngineAdam
+
+    def make(fused):
+        over = dict(n_envs=64, n_steps=32, model_id=model_id, fused_update=fused, max_grad_norm=0.05)   # small max norm: the clip is active
+        over.update(dict(batch_size=512, n_epochs=3) if algo == "ppo" else dict(batch_size=2048))
+        cfg = _cfg("CartPole-v1", "ppo" if algo == "ppo" else "reinforce", **over)
+        agent = build_agent(cfg, rank=0, world_size=1)
+        if not fused:        # reference optimizer: torch.optim.Adam on the per-tensor parameter views
+            agent._optimizer = torch.optim.Adam(agent.policy_model.parameters(), lr=cfg.policy_lr)
+        return agent
+
+    a, b = make(True), make(False)
+    assert isinstance(a.optimizers(), EngineAdam) and not isinstance(b.optimizers(), EngineAdam)
+    np.testing.assert_array_equal(a.policy_model.flat_params.cpu().numpy(), b.policy_model.flat_params.cpu().numpy())
+    for _ in range(2):
+        ta, tb = a.train_one_rollout(), b.train_one_rollout()
+        np.testing.assert_array_equal(ta.tm["obs"].cpu().numpy(), tb.tm["obs"].cpu().numpy())   # same weights -> same rollout
+        wa, wb = a.policy_model.flat_params.cpu().numpy(), b.policy_model.flat_params.cpu().numpy()
+        np.testing.assert_allclose(wa, wb, rtol=2e-5, atol=2e-6)
+        ma, mb = a.pop_epoch_metrics(), b.pop_epoch_metrics()
+        for k in ("opt/loss/total", "opt/grads/norm/all", "opt/grads/norm/backbone", "opt/grads/clip_coef", "opt/policy/entropy",
+                  "opt/activations/backbone.0/mean"):
+            np.testing.assert_allclose(ma[k], mb[k], rtol=1e-4, atol=1e-7, err_msg=k)
+        assert ma["opt/grads/clip_coef"] < 1.0
+    # optimizer state: torch.optim.Adam's layout, same moments
+    sa, sb = a.optimizers().state_dict(), b.optimizers().state_dict()
+    assert set(sa["state"].keys()) == set(sb["state"].keys())
+    for i in sa["state"]:
+        assert float(sa["state"][i]["step"]) == float(sb["state"][i]["step"])
+        np.testing.assert_allclose(sa["state"][i]["exp_avg"].cpu().numpy(), sb["state"][i]["exp_avg"].cpu().numpy(), rtol=1e-4, atol=1e-9)
+    # the engine optimizer loads a torch.optim.Adam checkpoint and keeps stepping
+    a.optimizers().load_state_dict(sb)
+    assert int(a.optimizers().step_dev.item()) == int(float(sb["state"][0]["step"]))
+    a.train_one_rollout()
+    assert np.isfinite(a.policy_model.flat_params.cpu().numpy()).all()
+
+
+def test_fused_step_is_skipped_for_overridden_losses():
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.agents.ppo.ppo_agent import PPOAgent
+
+    calls = []
+
+    class MyAgent(PPOAgent):
+        def losses_for_batch(self, batch, batch_idx):
+            calls.append(batch_idx)
+            return super().losses_for_batch(batch, batch_idx)
+
+    cfg = _cfg(n_envs=8, n_steps=32, batch_size=128, n_epochs=2, model_id="mlp_64x64")
+    agent = MyAgent(cfg, rank=0, world_size=1)
+    agent.train_one_rollout()
+    assert len(calls) == 4
+
+
+def test_two_gpu_peer_gradient_exchange():
+    """NVLink peer exchange of gs_update_finish vs the NCCL path on 2 ranks (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29741", os.path.join(root, "tests", "dist_peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "PEER_CHECK_OK" in r.stdout
