@@ -256,6 +256,8 @@ class BaseAgent(nn.Module):
 
     def _global_moments(self, b: EngineBatch):
         """Moments of the GLOBAL minibatch for a sharded step: those prepared up front, else prepare + all-reduce now."""
+        if b.moments is not None:
+            return b.moments
         if self.world_size <= 1 or not any(self._step_moments()):
             return None
         if b.moments is None:
@@ -373,10 +375,48 @@ class BaseAgent(nn.Module):
         self._pack_rollout(traj)
         key = _mix64(int(self.config.seed) ^ (self.current_epoch * 0x100000001B3))
         batches = [b for _, _, b in self.minibatches(traj, key)]
-        if self.world_size > 1 and any(self._step_moments()) and batches and self._fused_step_ok(batches[0]):
+        fused = bool(batches) and self._fused_step_ok(batches[0])
+        if fused and self.world_size > 1 and any(self._step_moments()):
             self._prepare_all(batches)
+        elif fused and tuple(getattr(self.config, "hidden_dims", ())) == (64, 64) and len(batches) > 1:
+            return self._train_pipelined(batches)
         for k, batch in enumerate(batches):
             self.training_step(batch, k)
+
+    def _train_pipelined(self, batches) -> None:
+        """One rank, tensor-core kernel: the gather pass of minibatch k+1 (sample-id translation + minibatch moments; independent
+        of the weights) runs on a side stream while minibatch k is in its update kernel / step tail, so it leaves the
+        critical path.  Two offset buffers; events order gather(k+2) after step(k) and step(k) after gather(k)."""
+        n, B = len(batches), self.local_batch_size
+        st = getattr(self, "_pipe", None)
+        if st is None or st["mom"].shape[0] < n or st["offs"].shape[1] != B:
+            st = self._pipe = dict(side=torch.cuda.Stream(device=self.device), offs=torch.empty(2, B, dtype=torch.int32, device=self.device),
+                                   mom=torch.zeros(n, 6, dtype=torch.float64, device=self.device),
+                                   gathered=[torch.cuda.Event() for _ in range(n)], stepped=[torch.cuda.Event() for _ in range(n)])
+        side, main = st["side"], torch.cuda.current_stream(self.device)
+        want = any(self._step_moments())
+
+        def gather(k):
+            b = batches[k]
+            b.struct.offsets = N.ptr(st["offs"][k & 1])
+            with torch.cuda.stream(side):
+                if k >= 2:
+                    side.wait_event(st["stepped"][k - 2])        # the update kernel of minibatch k-2 has read this offset buffer
+                self._prepare(b, st["mom"][k])
+                st["gathered"][k].record(side)
+            if not want:
+                b.moments = None
+
+        side.wait_stream(main)                                      # the rollout's targets and packed records are complete
+        gather(0)
+        gather(1)
+        for k, b in enumerate(batches):
+            main.wait_event(st["gathered"][k])
+            self.training_step(b, k)
+            st["stepped"][k].record(main)
+            if k + 2 < n:
+                gather(k + 2)
+        main.wait_stream(side)
 
     def train_one_rollout(self) -> DeviceTrajectory:
         """collect + targets + all minibatch passes: the unit the headline metric counts env-steps over."""

@@ -297,6 +297,16 @@ __device__ __forceinline__ void forward_heads(const float* sm, int s, float (&ou
     }
 }
 
+// Transcendentals of the per-sample loss: full-precision libm-style by default; a translation unit may opt into the SFU
+// approximations (ex2.approx / lg2.approx based, ~2^-21 relative) by defining GS_FAST_TRANSCENDENTALS before this header.
+#ifdef GS_FAST_TRANSCENDENTALS
+#define GS_EXPF(x) __expf(x)
+#define GS_LOGF(x) __logf(x)
+#else
+#define GS_EXPF(x) expf(x)
+#define GS_LOGF(x) logf(x)
+#endif
+
 // log-softmax over A <= 3 logits exactly as torch: x - (max + log(sum(exp(x - max))))
 __device__ __forceinline__ void log_softmax(const float* logits, int A, float* logp) {
     float mx = logits[0];
@@ -306,8 +316,8 @@ __device__ __forceinline__ void log_softmax(const float* logits, int A, float* l
     float se = 0.0f;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-        if (k < A) se += expf(logits[k] - mx);
-    const float lse = mx + logf(se);
+        if (k < A) se += GS_EXPF(logits[k] - mx);
+    const float lse = mx + GS_LOGF(se);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         if (k < A) logp[k] = logits[k] - lse;

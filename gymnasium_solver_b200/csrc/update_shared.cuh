@@ -69,13 +69,13 @@ __device__ __forceinline__ void sample_loss(const float (&out)[kNH], int A, int 
     float H = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-        if (k < A) { p[k] = expf(lp[k]); H -= p[k] * lp[k]; }
+        if (k < A) { p[k] = GS_EXPF(lp[k]); H -= p[k] * lp[k]; }
     const float logp = a_s == 0 ? lp[0] : (a_s == 1 ? lp[1] : lp[2]);
     float dlogp;
     float ratio_ppo = 0.f;
     if (ALGO == ALGO_PPO) {
         const float adv_n = hp.normalize_adv ? (adv_s - adv_mean) / adv_den : adv_s;
-        const float ratio = expf(logp - lp_old);
+        const float ratio = GS_EXPF(logp - lp_old);
         ratio_ppo = ratio;
         const float rc = fminf(fmaxf(ratio, hp.clip_lo), hp.clip_hi);
         const float s1 = adv_n * ratio, s2 = adv_n * rc;

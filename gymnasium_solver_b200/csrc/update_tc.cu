@@ -408,8 +408,8 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     tcu::compute_sync();
 
     // Metric partial sums and head-bias gradients: quantity q (q < PM_N: metric partial q, PM_N + r: bias gradient r) is
-    // reduced by the chunk-(q & 3) warp of each row quadrant (all four compute the row's loss anyway): after a butterfly sum
-    // over the warp's 32 rows, lane q keeps it -> ONE register instead of 26, and the work is spread over all 16 warps.
+    // reduced by the chunk-(q & 3) warp of each row quadrant (all four compute the row's loss anyway): after a transposing
+    // butterfly over the warp's 32 rows, lane q >> 2 keeps it -> ONE register instead of 26, the work spread over all 16 warps.
     float macc = 0.f;
     float zs0 = 0.f, zq0 = 0.f, zs1 = 0.f, zq1 = 0.f;
     uint32_t dead0 = 0, dead1 = 0;          // dead-unit counts of this warp's rows: lane i holds neuron 16*chunk + i
@@ -686,23 +686,42 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
             }
         }
         if (has_next) {
+            // Quantity q = 4 j + chunk (q < PM_N: metric term q of this row, PM_N + r: g[r]) is value j of this warp.  The 8 values
+            // are reduced over the warp's 32 rows by a transposing butterfly: each xor level halves the number of live values
+            // (a lane keeps the half its lane bit selects and sends the other), 4 + 2 + 1 + 1 + 1 = 9 shuffles in 5 dependent
+            // levels instead of 7 x 5; lane L ends with the warp total of value L & 7.
+            float v[8];
+            auto pick = [&](auto ctag) {
+                constexpr int Cc = decltype(ctag)::value;
 #pragma unroll
-            for (int i = 0; i < PM_N; ++i) {
-                if ((i & 3) != chunk) continue;
-                constexpr bool kPpoOnly[PM_N] = {false, true, false, true, true, true, true, true, true, false, false, false, false,
-                                                 false, false, false, false, false, false, false, false, false};
-                const bool z_stat = i == PM_Z0 || i == PM_Z0SQ || i == PM_Z1 || i == PM_Z1SQ;
-                const bool rf_only = i == PM_TGT || i == PM_TGT2 || i == PM_RETN || i == PM_RETN2;
-                if (z_stat || (ALGO == ALGO_PPO && rf_only) || (ALGO == ALGO_REINFORCE && kPpoOnly[i])) continue;
-                const float t = warp_sum(pl_keep[i]);
-                if (lane == i) macc += t;
+                for (int j = 0; j < 8; ++j) {
+                    const int q = 4 * j + Cc;                            // a constant after unrolling
+                    float x = 0.f;
+                    if (q < PM_N) x = pl_keep[q < PM_N ? q : 0];
+                    else if (q < PM_N + 4) x = g[(q - PM_N) & 3];
+                    v[j] = x;
+                }
+            };
+            if (chunk == 0) pick(std::integral_constant<int, 0>{});
+            else if (chunk == 1) pick(std::integral_constant<int, 1>{});
+            else if (chunk == 2) pick(std::integral_constant<int, 2>{});
+            else pick(std::integral_constant<int, 3>{});
+            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+            float w4[4], u2[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float keep = b0 ? v[2 * j + 1] : v[2 * j], send = b0 ? v[2 * j] : v[2 * j + 1];
+                w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (((PM_N + r) & 3) != chunk) continue;
-                const float t = warp_sum(g[r]);
-                if (lane == PM_N + r) macc += t;
+            for (int j = 0; j < 2; ++j) {
+                const float keep = b1 ? w4[2 * j + 1] : w4[2 * j], send = b1 ? w4[2 * j] : w4[2 * j + 1];
+                u2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
+            float t = (b2 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u2[0] : u2[1], 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            macc += t;
         }
         if (row_owner) {                                             // Y is free: every thread waited for the previous tail in B1
 #pragma unroll
@@ -727,9 +746,10 @@ update_tc_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_
     flush_wgrad(lane_addr, quad, chunk, lane, row, m.D, A, m.has_value, out, n_my <= kFlushTiles);
     // ---- block reductions through shared-memory atomics: head biases (4 floats) and the metric partials (PM_N doubles) ------
     float* fr = reinterpret_cast<float*>(red + PM_N);            // [4 quadrants][4 heads] bias-gradient partials
-    if (lane < PM_N + 4 && (lane & 3) == chunk) {
-        if (lane < PM_N) { if (macc != 0.f) atomicAdd(red + lane, (double)macc); }
-        else fr[quad * 4 + (lane - PM_N)] = macc;
+    if (lane < 8 && 4 * lane + chunk < PM_N + 4) {               // lane L holds quantity 4 L + chunk (see F3)
+        const int q = 4 * lane + chunk;
+        if (q < PM_N) { if (macc != 0.f) atomicAdd(red + q, (double)macc); }
+        else fr[quad * 4 + (q - PM_N)] = macc;
     }
     if (TRACK) {
         const double a0 = warp_sum((double)zs0), a1 = warp_sum((double)zq0), a2 = warp_sum((double)zs1), a3 = warp_sum((double)zq1);
