@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an ncu source-page capture by CUDA source line.
 
-usage: line_profile.py <report.ncu-rep> <cubin> <mangled-kernel-substring> [top]
+usage: line_profile.py <report.ncu-rep> <cubin> <mangled-kernel-substring> [top] [ncu kernel-name regex when the report holds several kernels]
 
 ncu's `--page source --print-source sass` gives per-SASS-instruction samples; `nvdisasm -g` gives the source line of every
 SASS instruction of the same cubin.  Joining them by instruction index yields samples / executed instructions / stall
@@ -25,7 +25,8 @@ for ln in sass:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[5], "--launch-count", "1"] if len(sys.argv) > 5 else []
+out = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
