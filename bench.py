@@ -212,6 +212,7 @@ def run_b200(args):
                        "batch_size_total": args.batch_size * world, "minibatches_per_step": (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs),
                        "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded; gradient mean per minibatch over NVLink peer memory inside gs_update_finish"
                                       if agent._peer is not None else f"dp{world}: envs sharded" + ("; NCCL grad all-reduce per minibatch" if world > 1 else ""),
+                       "grad_allreduce": agent.grad_allreduce_mode,
                        "l2": "rollout working set (>=300 MB per GPU) exceeds the 126 MB L2; no explicit flush",
                        "last_policy_loss": epoch_metrics.get("opt/loss/policy"), "last_ep_rew_mean": roll_metrics.get("roll/ep_rew/mean")},
             "clocks": clocks,
@@ -253,37 +254,51 @@ def kernel_rooflines(agent, cfg, dev):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps * 1e-3
 
-    # fused update kernel (+ its two tiny reduction kernels): one minibatch per call, a different minibatch every call
+    # the update kernel ALONE: every minibatch is prepared first (gather pass: sample offsets + minibatch moments into its own
+    # buffers), so a timed call launches only update_tc_kernel (deferred reduction); a different minibatch every call
     agent._pack_rollout(traj)          # as train_on_rollout does: 64-byte sample records for the tensor-core kernel's gather
-    batches = [b for _, _, b in agent.minibatches(traj, 12345)]
+    batches = [b for _, _, b in agent.minibatches(traj, 12345)][:8]
+    hd = tuple(cfg.hidden_dims)
+    tensor_path = hd == (64, 64) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
+    if tensor_path:
+        offs = torch.empty(len(batches), agent.local_batch_size, dtype=torch.int32, device=dev)
+        mom = torch.zeros(len(batches), 6, dtype=torch.float64, device=dev)
+        for k, bb in enumerate(batches):
+            bb.struct.offsets = N.ptr(offs[k])
+            agent._prepare(bb, mom[k])
     it = [0]
 
     def one_update():
-        agent.losses_for_batch(batches[it[0] % len(batches)], 0)
+        bb = batches[it[0] % len(batches)]
+        agent._launch_step(bb, defer=True, moments=bb.moments)
         it[0] += 1
 
     t = timed(one_update)
-    hd = tuple(cfg.hidden_dims)
     flops = FLOP_PER_SAMPLE_PASS.get(hd, 27264) * agent.local_batch_size
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    tensor_path = hd == (64, 64) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("update_tc_kernel" if tensor_path else "update_kernel", {}).get("dram_bytes_per_launch")
     if tensor_path:
         # 144 tcgen05.mma (K=8 tf32) per 128-sample tile; two issuing warps sustain one MMA per ~33 cycles (probes/tc_rate.cu)
         tiles_per_sm = -(-(agent.local_batch_size // 128) // 148)
         mma_floor_s = tiles_per_sm * 144 * 33.0 / (peaks["sm_max_mhz"] * 1e6)
         out["update"] = {"kernel": "update_tc_kernel<PPO> (gs_ppo_step: tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)", "bound": "tensor",
                          "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"],
-                         "traffic": None,
-                         "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the 64x64 MLP) / time of the whole gs_ppo_step call "
-                                 "(gather pass + update kernel + partial reduction + metric finalisation); peak = measured dense bf16. "
+                         "traffic": traffic,
+                         "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the 64x64 MLP, 27,264 per sample) / average launch time of "
+                                 "update_tc_kernel alone (CUDA events on the launching stream, 20 launches on 8 different prepared minibatches); "
+                                 "peak = measured dense bf16 (burst: the kernel is timed alone); traffic = ncu dram bytes of one launch "
+                                 "(profiles/r1d_update_tc_and_finish_ncu_details.md; algorithmic 71 MB). "
                                  "fp32 parity (1e-4) costs 3 tf32 MMAs per product, and K=8 tf32 MMAs with N<=72 are bound by a per-instruction "
                                  f"floor, not by math: tensor-pipe floor of this launch {mma_floor_s * 1e3:.3f} ms; the rest is SIMT work between the "
-                                 f"MMAs (profiles/). Same arithmetic on the FMA pipe (GS_UPDATE_IMPL=simt): 1.09 ms; fp32 FMA peak {fp32_peak:.1f} TF/s",
+                                 f"MMAs (profiles/r1d_*). Same arithmetic on the FMA pipe (GS_UPDATE_IMPL=simt): 1.09 ms; fp32 FMA peak {fp32_peak:.1f} TF/s",
                          "algorithmic_flop_per_launch": flops, "avg_launch_s": t, "tensor_pipe_floor_s": mma_floor_s,
                          "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}
     else:
         out["update"] = {"kernel": f"update_kernel<{hd}> (gs_ppo_step, fp32 FMA pipe)", "bound": "tensor", "achieved": flops / t / 1e12,
-                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": traffic,
                          "note": f"fp32 FMA-pipe kernel: fp32 FMA peak {fp32_peak:.1f} TF/s = 148 SM x 128 FMA x 2 x sm_max_mhz, of which "
                                  f"{flops / t / 1e12 / fp32_peak:.3f}",
                          "algorithmic_flop_per_launch": flops, "avg_launch_s": t, "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}

@@ -23,6 +23,7 @@ import ctypes as C
 import json
 import math
 import os
+import sys
 import time
 from pathlib import Path
 from typing import Any, Dict, Optional
@@ -152,11 +153,22 @@ class BaseAgent(nn.Module):
         self._metrics_n = 0
         self._moments = None
         self._mom_scratch = torch.zeros(6, dtype=torch.float64, device=self.device)
-        # NVLink peer exchange for the gradient mean (gs_update_finish); "nccl" keeps torch.distributed on the generic path
+        # NVLink peer exchange for the gradient mean (gs_update_finish).  grad_allreduce: "peer" (required), "nccl" (generic path:
+        # torch.distributed all-reduce between the step and clip / optimizer kernels), "auto" (peer, else nccl on every rank).
         self._peer = None
-        if self.world_size > 1 and bool(getattr(config, "fused_update", True)) and getattr(config, "grad_allreduce", "peer") == "peer":
-            P = int(self.policy_model.flat_params.numel())
-            self._peer = PeerGroup(self.rank, self.world_size, P, self.device)
+        self.grad_allreduce_mode = "none" if self.world_size == 1 else "nccl"
+        mode = getattr(config, "grad_allreduce", "auto")
+        if mode not in ("auto", "peer", "nccl"):
+            raise ValueError(f"grad_allreduce must be auto, peer or nccl, got {mode!r}")
+        if self.world_size > 1 and bool(getattr(config, "fused_update", True)) and mode in ("auto", "peer"):
+            try:
+                self._peer = PeerGroup(self.rank, self.world_size, int(self.policy_model.flat_params.numel()), self.device)
+                self.grad_allreduce_mode = "peer"
+            except N.EngineError as e:
+                if mode == "peer":
+                    raise
+                if self.rank == 0:
+                    print(f"[gymnasium_solver_b200] peer gradient exchange unavailable ({e}); using the NCCL all-reduce path", file=sys.stderr, flush=True)
 
     # ------------------------------------------------------------------------------------------------ construction
     def build_env(self, stage: str, **kwargs):

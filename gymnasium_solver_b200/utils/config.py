@@ -77,7 +77,8 @@ class Config:
     minibatch_shuffle: str = "device"     # "device": keyed bijection inside the kernel; "torch": argsort(rand) index tensors
     track_activations: bool = True
     fused_update: bool = True             # step tail (reduction, gradient exchange, clip, Adam) as ONE launch (gs_update_finish)
-    grad_allreduce: str = "peer"          # several ranks: "peer" = NVLink P2P exchange inside gs_update_finish; "nccl" = torch.distributed
+    grad_allreduce: str = "auto"          # several ranks: "peer" = NVLink P2P exchange inside gs_update_finish; "nccl" = torch.distributed;
+                                          # "auto" = peer when every rank can map every other rank's buffer, else nccl
     _hidden_dims: Optional[Tuple[int, ...]] = field(default=None, init=False, repr=False)
     _activation: Optional[str] = field(default=None, init=False, repr=False)
     _policy_kwargs: Optional[Dict[str, Any]] = field(default=None, init=False, repr=False)

@@ -57,15 +57,23 @@ class PeerGroup:
             raise N.EngineError(f"peer exchange supports 2..{N.PEER_MAX_WORLD} ranks, got {world_size}")
         self._N, self.handle = N, C.c_void_p()
         mine = (C.c_ubyte * N.PEER_HANDLE_BYTES)()
-        N.check(N.lib().gs_peer_create(rank, world_size, int(max_floats), int(device.index), C.byref(self.handle), mine))
+        err = None
         try:
-            gathered = exchange_handles(bytes(mine), world_size, device, group)
-            N.check(N.lib().gs_peer_connect(self.handle, gathered))
-        except Exception:
+            N.check(N.lib().gs_peer_create(rank, world_size, int(max_floats), int(device.index), C.byref(self.handle), mine))
+        except N.EngineError as e:
+            err = e
+        # every rank goes through the same collectives whatever happened locally, then all agree on success or failure
+        gathered = exchange_handles(bytes(mine), world_size, device, group)
+        if err is None:
+            try:
+                N.check(N.lib().gs_peer_connect(self.handle, gathered))
+            except N.EngineError as e:
+                err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # also the barrier: nobody signals before every rank has mapped every buffer
+        if int(ok.item()) == 0:
             self.close()
-            raise
-        if dist.is_initialized():
-            dist.barrier(group=group)        # nobody signals before every rank has mapped every buffer
+            raise N.EngineError(f"NVLink peer group could not be set up on every rank (rank {rank}: {err or 'ok'})")
 
     def close(self) -> None:
         if self.handle:
