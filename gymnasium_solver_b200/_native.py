@@ -95,6 +95,9 @@ SIGNATURES = {
     "gs_env_num_envs": (_i64, [_vp]),
     "gs_env_set_state": (_i32, [_vp, _vp, _vp, _vp]),
     "gs_env_get_state": (_i32, [_vp, _vp, _vp, _vp]),
+    "gs_env_snapshot_bytes": (_i64, [_vp]),
+    "gs_env_save": (_i32, [_vp, _vp, _vp]),
+    "gs_env_load": (_i32, [_vp, _vp, _vp]),
     "gs_env_reset": (_i32, [_vp, _vp, _vp]),
     "gs_env_step": (_i32, [_vp] * 9),
     "gs_wrapper_attach": (_i32, [_vp, _i32, C.POINTER(_f64), _i32]),

@@ -28,6 +28,7 @@ import time
 from pathlib import Path
 from typing import Any, Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -582,20 +583,26 @@ class BaseAgent(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, checkpoint_dir) -> None:
-        """model.pt / optimizer.pt / state.json like the reference (agents/base_agent.py:658-732), plus the device env
-        state and RNG counters the reference cannot resume (TODO.md:29)."""
+        """model.pt / optimizer.pt / state.json like the reference (agents/base_agent.py:658-732), plus what the reference cannot
+        resume (TODO.md:29): an exact snapshot of this rank's device envs (physics state, episode accumulators, autoreset flags,
+        reset-stream counters, count-bonus tables), the collector's current observations and running statistics.  Resuming from
+        it continues the run bit for bit.  Rank 0 writes the shared files, every rank its own env shard."""
         d = Path(checkpoint_dir)
         d.mkdir(parents=True, exist_ok=True)
-        torch.save(self.policy_model.state_dict(), d / "model.pt")
-        torch.save(self.optimizers().state_dict(), d / "optimizer.pt")
         col = self.get_rollout_collector("train")
-        env_state, elapsed = self.get_env("train").get_state()
-        torch.save({"state": env_state.cpu(), "elapsed": elapsed.cpu(), "obs": None if col.obs is None else col.obs.cpu()}, d / "env_state.pt")
-        state = {"epoch": self.current_epoch, "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
-                 "best_episode_reward": col._best_episode_reward if math.isfinite(col._best_episode_reward) else None,
-                 "best_eval_reward": self.best_eval_reward if math.isfinite(self.best_eval_reward) else None,
-                 "algo_id": self.config.algo_id, "env_id": self.config.env_id, "rng_seed": col.rng_seed}
-        (d / "state.json").write_text(json.dumps(state, indent=2))
+        col._resolve_pending_episodes()
+        if self.rank == 0:
+            torch.save(self.policy_model.state_dict(), d / "model.pt")
+            torch.save(self.optimizers().state_dict(), d / "optimizer.pt")
+            state = {"epoch": self.current_epoch, "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
+                     "best_episode_reward": col._best_episode_reward if math.isfinite(col._best_episode_reward) else None,
+                     "best_eval_reward": self.best_eval_reward if math.isfinite(self.best_eval_reward) else None,
+                     "algo_id": self.config.algo_id, "env_id": self.config.env_id, "rng_seed": col.rng_seed, "world_size": self.world_size}
+            (d / "state.json").write_text(json.dumps(state, indent=2))
+        env = self.get_env("train")
+        torch.save({"snapshot": env.snapshot().cpu(), "obs": None if col.obs is None else col.obs.cpu(),
+                    "stats": None if col._stats_dev is None else col._stats_dev.cpu(), "n_envs": env.num_envs,
+                    "env_id_offset": self.shard.env_id_offset}, d / f"env_state.rank{self.rank}.pt")
 
     def load_checkpoint(self, checkpoint_dir, *, resume_training: bool = True) -> None:
         d = Path(checkpoint_dir)
@@ -611,3 +618,14 @@ class BaseAgent(nn.Module):
             col._best_episode_reward = float(state["best_episode_reward"])
         if state.get("best_eval_reward") is not None:
             self.best_eval_reward = float(state["best_eval_reward"])
+        shard = d / f"env_state.rank{self.rank}.pt"
+        if shard.exists() and int(state.get("world_size", 1)) == self.world_size:      # same sharding: continue bit for bit
+            es = torch.load(shard, map_location="cpu")
+            if es["obs"] is not None:
+                col._sync_device_and_prepare_buffers()
+                self.get_env("train").restore(es["snapshot"])
+                col.obs.copy_(es["obs"].to(self.device))
+                if es.get("stats") is not None:
+                    col._stats_dev.copy_(es["stats"].to(self.device))
+                    col._stats_synced = np.zeros_like(col._stats_synced)
+                    col._flush_stats()

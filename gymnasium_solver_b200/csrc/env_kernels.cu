@@ -163,6 +163,42 @@ int gs_env_get_state(gs_env_t* e, double* state, int32_t* elapsed, void* stream)
     return 0;
 }
 
+// ---- exact snapshot of everything a handle holds on the device (checkpoint / resume) -------------------------------------
+// blob layout (8-byte aligned sections): state [S][N] f64 | ep_ret [N] f64 | elapsed [N] i32 | ep_len [N] i32 |
+// reset_count [N] u32 | needs_reset [N] u8 | StateCountBonus tables [N][pb*vb] u32 (when attached)
+static size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
+static size_t counts_bytes(const gs_env* e) {
+    if (e->params.wrapper != GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS || !e->params.counts) return 0;
+    return sizeof(uint32_t) * (size_t)e->params.wp[0] * (size_t)e->params.wp[1] * (size_t)e->n;
+}
+int64_t gs_env_snapshot_bytes(const gs_env_t* e) {
+    if (!e) GS_FAIL("gs_env_snapshot_bytes: NULL argument");
+    const size_t n = (size_t)e->n;
+    return (int64_t)(pad8(sizeof(double) * state_dim(e->kind) * n) + pad8(sizeof(double) * n) + 3 * pad8(4 * n) + pad8(n) + pad8(counts_bytes(e)));
+}
+static int snapshot_copy(gs_env* e, char* blob, bool save, cudaStream_t st) {
+    const size_t n = (size_t)e->n;
+    struct Sec { void* p; size_t bytes; } secs[] = {
+        {e->state, sizeof(double) * state_dim(e->kind) * n}, {e->ep_ret, sizeof(double) * n}, {e->elapsed, 4 * n}, {e->ep_len, 4 * n},
+        {e->reset_count, 4 * n}, {e->needs_reset, n}, {e->params.counts, counts_bytes(e)}};
+    for (const Sec& s : secs) {
+        if (s.bytes) {
+            if (save) GS_CUDA(cudaMemcpyAsync(blob, s.p, s.bytes, cudaMemcpyDeviceToDevice, st));
+            else GS_CUDA(cudaMemcpyAsync(s.p, blob, s.bytes, cudaMemcpyDeviceToDevice, st));
+        }
+        blob += pad8(s.bytes);
+    }
+    return 0;
+}
+int gs_env_save(gs_env_t* e, void* blob, void* stream) {
+    if (!e || !blob) GS_FAIL("gs_env_save: NULL argument");
+    return snapshot_copy(e, (char*)blob, true, (cudaStream_t)stream);
+}
+int gs_env_load(gs_env_t* e, const void* blob, void* stream) {
+    if (!e || !blob) GS_FAIL("gs_env_load: NULL argument");
+    return snapshot_copy(e, (char*)blob, false, (cudaStream_t)stream);
+}
+
 int gs_env_reset(gs_env_t* e, float* obs, void* stream) {
     if (!e || !obs) GS_FAIL("gs_env_reset: NULL argument");
     const unsigned blocks = (unsigned)((e->n + kEnvThreads - 1) / kEnvThreads);

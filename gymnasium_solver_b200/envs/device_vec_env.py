@@ -140,6 +140,26 @@ class DeviceVecEnv:
             N.check(N.lib().gs_env_get_state(self.handle, N.ptr(s), N.ptr(e), N.stream()))
         return s, e
 
+    # ---- exact snapshot (checkpoint / resume) ------------------------------------------------------------------------
+    def snapshot(self) -> torch.Tensor:
+        """Everything the handle holds on the device as one uint8 tensor (gs_env_save)."""
+        nbytes = N.lib().gs_env_snapshot_bytes(self.handle)
+        if nbytes <= 0:
+            raise N.EngineError(N.lib().gs_last_error().decode())
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_env_save(self.handle, N.ptr(blob), N.stream()))
+        return blob
+
+    def restore(self, blob: torch.Tensor) -> None:
+        nbytes = N.lib().gs_env_snapshot_bytes(self.handle)
+        if blob.dtype != torch.uint8 or blob.numel() != nbytes:
+            raise ValueError(f"snapshot of {blob.numel()} bytes does not fit this env ({nbytes} bytes: kind, size or wrapper differ)")
+        blob = blob.to(self.device).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_env_load(self.handle, N.ptr(blob), N.stream()))
+            torch.cuda.current_stream().synchronize()
+
     # ---- EnvInfoWrapper surface used by callbacks (gym_wrappers/env_info.py) -----------------------------------------
     def get_return_threshold(self):
         try:

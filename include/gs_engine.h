@@ -196,6 +196,13 @@ int64_t gs_env_num_envs(const gs_env_t* env);
 /* parity hooks: inject / read the fp64 SoA state [S][N] (+ TimeLimit elapsed steps, nullable) */
 int gs_env_set_state(gs_env_t* env, const double* state, const int32_t* elapsed, void* stream);
 int gs_env_get_state(gs_env_t* env, double* state, int32_t* elapsed, void* stream);
+/* Exact snapshot / restore of everything the handle holds on the device (physics state, TimeLimit and
+ * RecordEpisodeStatistics accumulators, autoreset flags, reset-stream counters, StateCountBonus tables): checkpoint / resume of
+ * the env side, which the reference cannot do (agents/base_agent.py:658-732 saves no env state; TODO.md:29).  blob is a
+ * caller-owned device buffer of gs_env_snapshot_bytes(); a blob only loads into a handle of the same kind, size and wrapper. */
+int64_t gs_env_snapshot_bytes(const gs_env_t* env);
+int gs_env_save(gs_env_t* env, void* blob, void* stream);
+int gs_env_load(gs_env_t* env, const void* blob, void* stream);
 /* VectorEnv.reset(): new episode in every env (rollout_collector.py:317); obs is (N,D) */
 int gs_env_reset(gs_env_t* env, float* obs, void* stream);
 /* VectorEnv.step(actions) (rollout_collector.py:504). ep_return/ep_length (nullable) carry

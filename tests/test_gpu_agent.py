@@ -278,3 +278,41 @@ def test_two_gpu_peer_gradient_exchange():
                         "--master-port", "29741", os.path.join(root, "tests", "dist_peer_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "PEER_CHECK_OK" in r.stdout
+
+
+@pytest.mark.parametrize("env,variant,over", [
+    ("CartPole-v1", "ppo", dict(n_envs=64, n_steps=32, batch_size=512, n_epochs=2, model_id="mlp_64x64", max_episode_steps=40)),
+    ("MountainCar-v0", "ppo", dict(n_envs=32, n_steps=48, batch_size=512, n_epochs=2, model_id="mlp_64x64", max_episode_steps=30)),
+    ("CartPole-v1", "reinforce", dict(n_envs=32, n_steps=64, batch_size=2048, model_id="mlp_64x64", max_episode_steps=25)),
+])
+def test_checkpoint_resume_continues_bit_for_bit(tmp_path, env, variant, over):
+    """weights + Adam state + device env snapshot (physics state, episode accumulators, autoreset flags, reset-stream
+    counters, count-bonus tables) + collector state -> a resumed run is bit-identical to the uninterrupted one."""
+    from gymnasium_solver_b200.agents import build_agent
+
+    cfg = _cfg(env, variant, **over)
+    a = build_agent(cfg, rank=0, world_size=1)
+    for _ in range(3):
+        a.train_one_rollout()
+        a.current_epoch += 1
+    a.save_checkpoint(tmp_path / "ck")
+    for _ in range(2):
+        ta = a.train_one_rollout()
+        a.current_epoch += 1
+    b = build_agent(cfg, rank=0, world_size=1)
+    b.load_checkpoint(tmp_path / "ck")
+    assert b.current_epoch == 3
+    for _ in range(2):
+        tb = b.train_one_rollout()
+        b.current_epoch += 1
+    for k in ("obs", "actions", "rewards", "dones", "adv", "ret"):
+        assert torch.equal(ta.tm[k], tb.tm[k]), k
+    assert torch.equal(a.policy_model.flat_params, b.policy_model.flat_params)
+    assert torch.equal(a.optimizers().exp_avg_sq, b.optimizers().exp_avg_sq)
+    sa, sb = a.get_env("train").snapshot(), b.get_env("train").snapshot()
+    assert torch.equal(sa, sb)
+    assert (tmp_path / "ck" / "env_state.rank0.pt").exists()
+    # a snapshot only loads into an env of the same kind / size / wrapper
+    other = build_agent(_cfg(env, variant, **{**over, "n_envs": over["n_envs"] * 2}), rank=0, world_size=1)
+    with pytest.raises(ValueError, match="does not fit"):
+        other.get_env("train").restore(sa)
