@@ -477,3 +477,76 @@ def test_two_phase_step_for_sharded_minibatches_matches_the_one_call_step(algo):
     for i, k in enumerate(N.METRIC_KEYS):
         if not k.startswith("opt/grads"):
             np.testing.assert_array_equal(mv[i], m_ref[k], err_msg=k)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_deferred_step_and_update_finish_match_reference_fixture(golden_dir, tag):
+    """C-ABI: gs_ppo_step with defer_reduce + gs_update_finish (ordered reduction, metrics, norms, clip, Adam in one launch) against
+    the reference-generated fixture (gradients before / after clip_grad_norm_, metrics) and torch.optim.Adam on the clipped gradient."""
+    import ctypes as C
+
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    d = np.load(os.path.join(golden_dir, f"policy_{tag}.npz"))
+    p = _params(d, "p_")
+    B = d["obs"].shape[0]
+    batch, keep = E.make_batch(1, B, E.cu(d["obs"][None]), E.cu(d["actions"][None].astype(np.int32)), E.cu(d["old_logp"][None]),
+                               E.cu(d["values_old"][None]), E.cu(d["adv"][None]), E.cu(d["ret"][None]))
+    # flat parameter vector in nn.Module.parameters() order; the gs_mlp_t points into it (what flatten_parameters_ does for a model)
+    order = [k for k in P.PARAM_ORDER if k in p]
+    flat = torch.cat([p[k].reshape(-1) for k in order]).to("cuda").contiguous()
+    views, off = {}, 0
+    for k in order:
+        n = p[k].numel()
+        views[k] = flat[off:off + n].view(p[k].shape)
+        off += n
+    m = N.mlp_struct_from_params(views)
+    Pn = int(N.lib().gs_mlp_param_count(C.byref(m)))
+    assert Pn == flat.numel()
+    wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    grads = torch.full((Pn,), float("nan"), device="cuda")
+    metrics = torch.zeros(N.N_METRICS, dtype=torch.float64, device="cuda")
+    msum = torch.zeros(N.N_METRICS, dtype=torch.float64, device="cuda")
+    hp = _ppo_hp(N, norm=True)
+    batch.defer_reduce = 1
+    L = N.lib()
+    N.check(L.gs_ppo_step(C.byref(m), C.byref(batch), C.byref(hp), None, N.ptr(grads), N.ptr(metrics), N.ptr(ws), wsb, N.stream()))
+    fin = N.GsFinish()
+    fin.algo, fin.track_activations, fin.normalize_adv, fin.normalize_ret = 0, hp.track_activations, 1, 0
+    fin.vf_coef, fin.ent_coef, fin.max_grad_norm = hp.vf_coef, hp.ent_coef, 0.5
+    # 1) no optimizer: grads_flat = clipped gradient, metrics complete, metrics_sum accumulates
+    w0 = flat.clone()
+    N.check(L.gs_update_finish(C.byref(m), C.byref(batch), C.byref(fin), N.ptr(grads), None, None, N.ptr(metrics), N.ptr(msum), N.ptr(ws), wsb, N.stream()))
+    E.sync()
+    assert torch.equal(flat, w0)
+    ref_clip = np.concatenate([d[f"ppo_batch_gc_{k}"].ravel() for k in P.PARAM_ORDER if f"ppo_batch_gc_{k}" in d.files])
+    _assert_grads_close(grads.cpu().numpy(), ref_clip)
+    mv = metrics.cpu().numpy()
+    mm = {k: mv[i] for i, k in enumerate(N.METRIC_KEYS)}
+    np.testing.assert_allclose(mm["opt/loss/total"], float(d["ppo_batch_loss"]), rtol=1e-4, atol=1e-6)
+    for k in PPO_METRICS:
+        np.testing.assert_allclose(mm[k], float(d[f"ppo_batch_m_{k}"]), rtol=1e-4, atol=2e-6, err_msg=k)
+    for grp in ("all", "backbone", "policy_head", "value_head"):
+        np.testing.assert_allclose(mm[f"opt/grads/norm/{grp}"], float(d[f"ppo_batch_m_opt/grads/norm/{grp}"]), rtol=1e-4)
+    np.testing.assert_array_equal(msum.cpu().numpy()[:32], mv[:32])
+    # 2) with Adam: the same call sequence again, parameters move like torch.optim.Adam on the clipped gradient
+    ref_p = w0.detach().cpu().clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    ref_p.grad = grads.detach().cpu().clone()
+    opt.step()
+    exp_avg, exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    adam = N.GsAdam()
+    adam.params_flat, adam.exp_avg, adam.exp_avg_sq, adam.step_count = N.ptr(flat), N.ptr(exp_avg), N.ptr(exp_avg_sq), N.ptr(step)
+    adam.lr, adam.beta1, adam.beta2, adam.eps = 1e-3, 0.9, 0.999, 1e-8
+    N.check(L.gs_ppo_step(C.byref(m), C.byref(batch), C.byref(hp), None, N.ptr(grads), N.ptr(metrics), N.ptr(ws), wsb, N.stream()))
+    N.check(L.gs_update_finish(C.byref(m), C.byref(batch), C.byref(fin), N.ptr(grads), C.byref(adam), None, N.ptr(metrics), N.ptr(msum), N.ptr(ws), wsb, N.stream()))
+    E.sync()
+    assert int(step.item()) == 1
+    np.testing.assert_allclose(flat.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(msum.cpu().numpy()[0], 2 * mv[0], rtol=1e-12)
+    # 3) errors fail loudly
+    with pytest.raises(N.EngineError, match="NULL"):
+        N.check(L.gs_update_finish(C.byref(m), C.byref(batch), C.byref(fin), None, None, None, N.ptr(metrics), None, N.ptr(ws), wsb, N.stream()))
