@@ -475,9 +475,11 @@ class BaseAgent(nn.Module):
 
     def train_one_rollout(self) -> DeviceTrajectory:
         """collect + targets + all minibatch passes: the unit the headline metric counts env-steps over."""
-        traj = self.get_rollout_collector("train").collect()
+        col = self.get_rollout_collector("train")
+        traj = col.collect()
         self._trajectories = traj
         self.train_on_rollout(traj)
+        col.resolve_episodes_async()      # host-side episode bookkeeping while the passes run (no drain at the next collect)
         return traj
 
     def pop_epoch_metrics(self) -> Dict[str, float]:

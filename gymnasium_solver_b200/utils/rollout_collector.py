@@ -185,6 +185,21 @@ class RolloutCollector:
         counts = self._action_counts_dev.cpu().numpy()
         self._action_counts = counts.copy() if counts.sum() > 0 else self._action_counts
 
+    def resolve_episodes_async(self) -> None:
+        """Episode bookkeeping of the last rollout on a SIDE stream that only waits for the collect / target kernels.  Called by the
+        agent after it has queued the rollout's minibatch passes: the host synchronisation inside (``nonzero`` needs a count) then
+        returns while the training stream still has the passes to run, instead of draining it at the next ``collect()``."""
+        if self._pending is None or not self._events_pending:
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._side_stream):
+            self._side_stream.wait_event(self._events[1])        # recorded after the rollout's last kernel (targets)
+            self._resolve_pending_episodes()
+            self._side_stream.synchronize()
+
+    _side_stream = None
+
     def _resolve_pending_episodes(self) -> None:
         """Episode bookkeeping of the last rollout (reference: _process_done_infos, rollout_collector.py:210-294),
         resolved lazily from the (T, N) ``dones`` / ``ep_return`` / ``ep_length`` arrays the collect kernel wrote."""
