@@ -108,8 +108,11 @@ policy_act_kernel(MlpDev m, const float* __restrict__ obs, int64_t n, uint64_t r
 }
 
 // ---- fused collect ----------------------------------------------------------------------------------------------------
+#ifndef GS_COLLECT_MIN_CTAS
+#define GS_COLLECT_MIN_CTAS 3
+#endif
 template <class C, int KIND>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (C::H1 <= 64 ? GS_COLLECT_MIN_CTAS : 1))   // 64-wide nets: 3 CTAs per SM (59.6 KB shared memory each) need <= 85 registers
 collect_kernel(EnvDev h, MlpDev m, RolloutDev buf, float* __restrict__ cur_obs, uint64_t rng_seed, uint64_t step0, int deterministic) {
     extern __shared__ __align__(16) float sm[];
     constexpr int D = EnvDims<KIND>::D;
