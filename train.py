@@ -2,7 +2,9 @@
 """``python train.py <env>:<variant> [--override KEY=VALUE]... [--max-env-steps N]`` (reference: train.py:30-148).
 
 Multi-GPU: ``python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 train.py <env>:<variant>``; each
-rank owns n_envs/N environments and gradients are averaged over NCCL once per minibatch."""
+rank owns n_envs/N environments; the gradient mean of every minibatch runs over NVLink peer memory inside the step's tail
+kernel (``grad_allreduce=nccl`` selects the torch.distributed path).  ``--checkpoint-dir`` / ``--resume`` save and continue a run
+bit for bit (weights, Adam state, device env snapshot per rank)."""
 from __future__ import annotations
 
 import argparse
@@ -78,8 +80,8 @@ def main(argv=None) -> int:
     if int(os.environ.get("RANK", 0)) == 0:
         print(f"Stopped: {result['stop_reason']}  epochs={result['epochs']}  env_steps={result['total_env_steps']}  "
               f"elapsed={result['elapsed_s']:.1f}s  best_eval={result['best_eval_reward']}")
-        if args.checkpoint_dir:
-            agent.save_checkpoint(args.checkpoint_dir)
+    if args.checkpoint_dir:                       # every rank: rank 0 writes the shared files, each rank its own env shard
+        agent.save_checkpoint(args.checkpoint_dir)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
