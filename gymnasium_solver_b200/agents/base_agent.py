@@ -392,7 +392,7 @@ class BaseAgent(nn.Module):
         tensor_path = tuple(getattr(self.config, "hidden_dims", ())) == (64, 64)
         if fused and self.world_size > 1 and any(self._step_moments()):
             per_pass = max(1, len(batches) // max(1, int(self.n_epochs)))
-            if tensor_path and len(batches) >= 3 * per_pass:
+            if tensor_path and per_pass >= 2 and len(batches) >= 2 * per_pass:
                 return self._train_pipelined_sharded(batches, per_pass)
             self._prepare_all(batches)
         elif fused and tensor_path and len(batches) > 1:
@@ -402,40 +402,51 @@ class BaseAgent(nn.Module):
 
     def _train_pipelined_sharded(self, batches, per_pass: int) -> None:
         """Several ranks, tensor-core kernel: the gather passes of pass p+1 (sample-id translation + local minibatch moments) and
-        the ONE all-reduce of that pass's moments run on a low-priority side stream while pass p is being trained, so only the
-        first pass's preparation is exposed.  Offset buffers: a ring of two passes."""
+        the ONE all-reduce of that pass's moments run on a side stream while pass p is being trained, so only the first pass's
+        preparation is exposed.  The gathers are queued one per training step (each runs in the shadow of a step tail, where one
+        block works and the other SMs idle) rather than eight at once in front of an update kernel.  Offset buffers: a ring of
+        two passes."""
         n, B = len(batches), self.local_batch_size
         n_chunks = (n + per_pass - 1) // per_pass
         st = getattr(self, "_pipe_sh", None)
         if st is None or st["mom"].shape[0] < n or st["offs"].shape != (2 * per_pass, B):
-            st = self._pipe_sh = dict(side=torch.cuda.Stream(device=self.device, priority=0),
+            st = self._pipe_sh = dict(side=torch.cuda.Stream(device=self.device),
                                       offs=torch.empty(2 * per_pass, B, dtype=torch.int32, device=self.device),
                                       mom=torch.zeros(n, 6, dtype=torch.float64, device=self.device),
                                       ready=[torch.cuda.Event() for _ in range(n_chunks)], done=[torch.cuda.Event() for _ in range(n_chunks)])
         side, main = st["side"], torch.cuda.current_stream(self.device)
+        bounds = lambda c: (c * per_pass, min(n, (c + 1) * per_pass))
 
-        def prepare_chunk(c):
-            lo, hi = c * per_pass, min(n, (c + 1) * per_pass)
+        def gather(c, k):                                           # minibatch k of pass c, on the side stream
+            lo, hi = bounds(c)
             with torch.cuda.stream(side):
-                if c >= 2:
+                if k == lo and c >= 2:
                     side.wait_event(st["done"][c - 2])              # pass c-2 has read this half of the offset ring
-                for k in range(lo, hi):
-                    b = batches[k]
-                    b.struct.offsets = N.ptr(st["offs"][(c & 1) * per_pass + (k - lo)])
-                    self._prepare(b, st["mom"][k])
-                allreduce_moments(st["mom"][lo:hi], self.world_size)  # statistics of the GLOBAL minibatches of this pass
-                st["ready"][c].record(side)
+                b = batches[k]
+                b.struct.offsets = N.ptr(st["offs"][(c & 1) * per_pass + (k - lo)])
+                self._prepare(b, st["mom"][k])
+                if k == hi - 1:
+                    allreduce_moments(st["mom"][lo:hi], self.world_size)   # statistics of the GLOBAL minibatches of this pass
+                    st["ready"][c].record(side)
 
         side.wait_stream(main)
-        prepare_chunk(0)
-        prepare_chunk(1)
+        for k in range(*bounds(0)):
+            gather(0, k)
         for c in range(n_chunks):
+            lo, hi = bounds(c)
+            nxt = list(range(*bounds(c + 1))) if c + 1 < n_chunks else []
             main.wait_event(st["ready"][c])
-            for k in range(c * per_pass, min(n, (c + 1) * per_pass)):
+            for k in range(lo, hi):
                 self.training_step(batches[k], k)
+                # one gather of the next pass per step; the last step of the pass gets none, so the pass's all-reduce (queued with
+                # its final gather, one step earlier) has a whole step to complete
+                take = 2 if k == hi - 2 else (0 if k == hi - 1 else 1)
+                for _ in range(take):
+                    if nxt:
+                        gather(c + 1, nxt.pop(0))
+            while nxt:
+                gather(c + 1, nxt.pop(0))
             st["done"][c].record(main)
-            if c + 2 < n_chunks:
-                prepare_chunk(c + 2)
         main.wait_stream(side)
 
     def _train_pipelined(self, batches) -> None:
