@@ -152,7 +152,6 @@ class BaseAgent(nn.Module):
         self._metrics_dev = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
         self._metrics_sum = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
         self._metrics_n = 0
-        self._moments = None
         self._mom_scratch = torch.zeros(6, dtype=torch.float64, device=self.device)
         # NVLink peer exchange for the gradient mean (gs_update_finish).  grad_allreduce: "peer" (required), "nccl" (generic path:
         # torch.distributed all-reduce between the step and clip / optimizer kernels), "auto" (peer, else nccl on every rank).
