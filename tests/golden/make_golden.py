@@ -9,12 +9,16 @@ What runs unmodified from /root/reference:
   utils/rollout_buffer.py      (RolloutBuffer.add + flatten_slice_env_major env-major order)
   utils/models.py + utils/policy_ops.py + utils/distributions.py (MLPActorCritic / MLPPolicy forward, policy_act)
   agents/ppo/ppo_agent.py, agents/reinforce/reinforce_agent.py (losses_for_batch + backward + grad norms)
+  gym_wrappers/MountainCarV0/state_count_bonus.py, gym_wrappers/MountainCarV0/reward_shaper.py,
+  gym_wrappers/CartPoleV1/reward_shaper.py (the per-env reward wrappers, stepped over a scripted sub-env that replays a
+  physics trajectory; see golden_wrappers)
 Shims: the reference's own Lightning stub (tests/conftest.py:15-81) and a stub `gymnasium` module (the real
 package is absent here); neither touches the arithmetic above.  REINFORCE needs config.normalize_advantages
 supplied because the reference reads a field REINFORCEConfig lacks.
 """
 from __future__ import annotations
 
+import json
 import os
 import sys
 import types
@@ -43,6 +47,16 @@ def _install_shims():
 
     for n in ("Wrapper", "ObservationWrapper", "ActionWrapper", "RewardWrapper", "Env"):
         setattr(gym, n, type(n, (_Base,), {}))
+
+    class _Wrapper:                     # gymnasium.Wrapper as far as the reward wrappers use it: keeps the inner env
+        def __init__(self, env):
+            self.env = env
+
+        @property
+        def unwrapped(self):
+            return getattr(self.env, "unwrapped", self.env)
+
+    gym.Wrapper = _Wrapper
     spaces = types.ModuleType("gymnasium.spaces")
     for n in ("Box", "Discrete", "MultiBinary", "MultiDiscrete", "Dict", "Tuple", "Space"):
         setattr(spaces, n, type(n, (_Base,), {}))
@@ -229,8 +243,80 @@ def golden_masked_categorical():
     print("masked categorical: ok")
 
 
+def golden_wrappers():
+    """The reference's reward wrappers, executed as shipped, over a scripted sub-env that replays one physics trajectory (produced by
+    oracle/envs.c WITHOUT a wrapper: the physics is not what is being pinned here) through the NEXT_STEP autoreset protocol of
+    SyncVectorEnv: after a done the vector env calls ``reset()`` on the wrapped sub-env instead of ``step()``.
+
+    numpy promotion: the reference pins numpy 1.26.4 (uv.lock), where a float32 scalar combined with a Python float promotes to
+    float64; this container has numpy 2.3 (NEP 50 keeps float32).  The wrappers only ever combine observation entries with Python
+    scalars, so feeding the float32-ROUNDED observations as float64 arrays reproduces the pinned behaviour exactly."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle.envs import OracleVecEnv
+    from gym_wrappers.CartPoleV1.reward_shaper import CartPoleV1_RewardShaper
+    from gym_wrappers.MountainCarV0.reward_shaper import MountainCarV0_RewardShaper
+    from gym_wrappers.MountainCarV0.state_count_bonus import MountainCarV0_StateCountBonus
+
+    class Scripted:
+        def __init__(self, obs0, script):
+            self.script, self.i, self.obs0, self.unwrapped = script, 0, obs0, self
+        def reset(self, **_):
+            if self.i == 0 and self.obs0 is not None:
+                o, self.obs0 = self.obs0, None
+                return o, {}
+            o = self.script[self.i][0]
+            self.i += 1
+            return o, {}
+        def step(self, action):
+            o, r, te, tr = self.script[self.i]
+            self.i += 1
+            return o, r, te, tr, {}
+
+    cases = [("mcar_count", "MountainCar-v0", MountainCarV0_StateCountBonus, dict(position_bins=50, velocity_bins=50, bonus_scale=0.1, bonus_type="count"), 30),
+             ("mcar_count_log", "MountainCar-v0", MountainCarV0_StateCountBonus, dict(position_bins=7, velocity_bins=5, bonus_scale=1.0, bonus_type="log", min_count=2), 25),
+             ("mcar_count_inverse", "MountainCar-v0", MountainCarV0_StateCountBonus, dict(position_bins=12, velocity_bins=9, bonus_scale=0.5, bonus_type="inverse"), 40),
+             ("mcar_shaper", "MountainCar-v0", MountainCarV0_RewardShaper, dict(position_reward_scale=100.0, velocity_reward_scale=10.0, height_reward_scale=50.0), 35),
+             ("cartpole_shaper", "CartPole-v1", CartPoleV1_RewardShaper, dict(angle_reward_scale=1.0, position_reward_scale=0.25, clip_potential=True), 500),
+             ("cartpole_shaper_noclip", "CartPole-v1", CartPoleV1_RewardShaper, dict(angle_reward_scale=0.7, position_reward_scale=1.5, clip_potential=False), 12)]
+    out = {}
+    T = 240
+    for tag, env_id, cls, kwargs, max_steps in cases:
+        seed = 100 + len(out)
+        phys = OracleVecEnv(env_id, 1, seed=seed, max_episode_steps=max_steps)
+        obs0, _ = phys.reset()
+        state0, elapsed0 = phys.get_state()
+        rng = np.random.default_rng(seed)
+        n_act = phys.single_action_space.n
+        actions = rng.integers(0, n_act, size=T).astype(np.int32)
+        script, base_r, dones = [], [], []
+        for t in range(T):
+            o, r, te, tr, _ = phys.step(actions[t:t + 1])
+            script.append((o[0].astype(np.float64), float(r[0]), bool(te[0]), bool(tr[0])))   # float32-rounded values as float64
+            base_r.append(float(r[0])); dones.append(bool(te[0] or tr[0]))
+        wrapped = cls(Scripted(obs0[0].astype(np.float64), script), **kwargs)
+        wrapped.reset()
+        shaped, prev_done = [], False
+        for t in range(T):
+            if prev_done:                       # SyncVectorEnv NEXT_STEP autoreset: reset instead of step, reward 0
+                wrapped.reset()
+                rew, te, tr = 0.0, False, False
+            else:
+                _, rew, te, tr, _ = wrapped.step(int(actions[t]))
+            shaped.append(float(rew))
+            prev_done = bool(te or tr)
+        assert sum(dones) >= 2, (tag, sum(dones))
+        params = {k: (v if not isinstance(v, str) else {"count": 0, "inverse": 1, "log": 2}[v]) for k, v in kwargs.items()}
+        out.update({f"{tag}_seed": np.int64(seed), f"{tag}_max_steps": np.int64(max_steps), f"{tag}_actions": actions,
+                    f"{tag}_state0": state0, f"{tag}_elapsed0": elapsed0, f"{tag}_base_reward": np.array(base_r),
+                    f"{tag}_reward": np.array(shaped), f"{tag}_done": np.array(dones),
+                    f"{tag}_kwargs": np.array(json.dumps({"id": cls.__name__, **kwargs}))})
+        print("wrapper:", tag, "episodes", sum(dones), "shaping abs mean", float(np.mean(np.abs(np.array(shaped) - np.array(base_r)))))
+    np.savez(os.path.join(OUT, "wrappers.npz"), **out)
+
+
 if __name__ == "__main__":
     _install_shims()
+    golden_wrappers()
     golden_returns()
     golden_buffer()
     golden_masked_categorical()

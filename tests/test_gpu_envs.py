@@ -117,3 +117,29 @@ def test_wrapper_errors_fail_loudly():
     arr = (C.c_double * 5)(50, 50, 0.1, 0, 1)
     assert N.lib().gs_wrapper_attach(g.h, 1, arr, 5) != 0  # MountainCar wrapper on CartPole
     assert b"does not apply" in N.lib().gs_last_error()
+
+
+@pytest.mark.parametrize("tag", ["mcar_count", "mcar_count_log", "mcar_count_inverse", "mcar_shaper", "cartpole_shaper", "cartpole_shaper_noclip"])
+def test_device_reward_wrappers_match_fixtures_generated_by_the_reference_wrappers(golden_dir, tag):
+    """The fused device wrappers (gs_wrapper_attach) against rewards produced by EXECUTING the reference's wrapper classes
+    (tests/golden/wrappers.npz, see tests/golden/make_golden.py::golden_wrappers): same Philox reset stream, same actions, several
+    episodes with autoresets; done flags exact, rewards within 1e-6."""
+    import json
+    import os
+
+    import engine_api as E
+
+    d = np.load(os.path.join(golden_dir, "wrappers.npz"))
+    spec = json.loads(str(d[f"{tag}_kwargs"]))
+    env_id = "CartPole-v1" if tag.startswith("cartpole") else "MountainCar-v0"
+    k, p = OE.wrapper_params(spec)
+    g = E.DevEnv(env_id, 1, seed=int(d[f"{tag}_seed"]), max_episode_steps=int(d[f"{tag}_max_steps"]), wrappers=[(k, list(p))])
+    g.reset()
+    s0, _ = g.get_state()
+    np.testing.assert_array_equal(s0, d[f"{tag}_state0"])
+    got, dones = [], []
+    for t, a in enumerate(d[f"{tag}_actions"]):
+        _, r, te, tr, _, _ = g.step(np.array([a], dtype=np.int32))
+        got.append(float(r[0])); dones.append(bool(te[0] or tr[0]))
+    np.testing.assert_array_equal(np.array(dones), d[f"{tag}_done"])
+    np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"].astype(np.float32), rtol=1e-6, atol=1e-6)

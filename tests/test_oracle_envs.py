@@ -2,6 +2,7 @@
 trajectories); these tests pin the generator (Random123 known answers), hand-derived single steps, and the
 TimeLimit / NEXT_STEP autoreset / RecordEpisodeStatistics bookkeeping the reference's collector depends on."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -175,3 +176,31 @@ def test_cartpole_reward_shaper_is_potential_difference():
         obs = nobs
         if term[0] or trunc[0]:
             break
+
+
+WRAPPER_TAGS = ["mcar_count", "mcar_count_log", "mcar_count_inverse", "mcar_shaper", "cartpole_shaper", "cartpole_shaper_noclip"]
+
+
+@pytest.mark.parametrize("tag", WRAPPER_TAGS)
+def test_reward_wrappers_match_fixtures_generated_by_the_reference_wrappers(golden_dir, tag):
+    """tests/golden/wrappers.npz holds rewards produced by EXECUTING the reference's wrapper classes
+    (gym_wrappers/MountainCarV0/state_count_bonus.py, MountainCarV0/reward_shaper.py, CartPoleV1/reward_shaper.py) over a scripted
+    sub-env replaying a physics trajectory through SyncVectorEnv's NEXT_STEP autoreset protocol.  The oracle with its restated
+    wrapper attached must reproduce them on the same trajectory (several episodes, persistent count tables, potentials re-based
+    at every reset)."""
+    import json
+
+    d = np.load(os.path.join(golden_dir, "wrappers.npz"))
+    spec = json.loads(str(d[f"{tag}_kwargs"]))
+    env_id = "CartPole-v1" if tag.startswith("cartpole") else "MountainCar-v0"
+    env = E.OracleVecEnv(env_id, 1, seed=int(d[f"{tag}_seed"]), max_episode_steps=int(d[f"{tag}_max_steps"]), env_wrappers=[spec])
+    env.reset()
+    s0, e0 = env.get_state()
+    np.testing.assert_array_equal(s0, d[f"{tag}_state0"])          # same physics start as the fixture's trajectory
+    got, dones = [], []
+    for a in d[f"{tag}_actions"]:
+        _, r, te, tr, _ = env.step(np.array([a], dtype=np.int32))
+        got.append(float(r[0])); dones.append(bool(te[0] or tr[0]))
+    np.testing.assert_array_equal(np.array(dones), d[f"{tag}_done"])
+    assert not np.allclose(d[f"{tag}_reward"], d[f"{tag}_base_reward"])          # the wrapper did something
+    np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"], rtol=0, atol=1e-12)
