@@ -39,6 +39,7 @@ from ..utils.optimizer_factory import EngineAdam, build_optimizer
 from ..utils.policy_factory import build_policy_from_env_and_config
 from ..utils.rollout_collector import DeviceTrajectory, RolloutCollector
 from ..utils.rollout_buffer import RolloutTrajectory
+from ..utils.schedules import position_to_env_steps, progress_fraction, scheduled_value
 
 STAGES = ["train", "val", "test"]
 _SPLITMIX = 0x9E3779B97F4A7C15
@@ -511,7 +512,7 @@ class BaseAgent(nn.Module):
         return max(0.0, min(total / float(self.config.max_env_steps), 1.0))
 
     def _apply_schedules(self) -> None:
-        """reference trainer_callbacks/hyperparameter_scheduler.py:76-113 (linear / cosine / exponential)."""
+        """reference trainer_callbacks/hyperparameter_scheduler.py:76-113 + utils/schedule_resolver.py (utils/schedules.py)."""
         cfg = self.config
         steps = self.get_rollout_collector("train").total_steps * self.world_size
         for param in ("policy_lr", "ent_coef", "vf_coef", "clip_range", "clip_range_vf"):
@@ -519,17 +520,13 @@ class BaseAgent(nn.Module):
             if not kind:
                 continue
             v0, v1 = getattr(cfg, f"{param}_schedule_start_value"), getattr(cfg, f"{param}_schedule_end_value")
-            p0, p1 = getattr(cfg, f"{param}_schedule_start"), getattr(cfg, f"{param}_schedule_end")
-            to_steps = lambda p: p * cfg.max_env_steps if p <= 1.0 else p
-            s0, s1 = to_steps(p0), to_steps(p1)
-            frac = min(1.0, max(0.0, (steps - s0) / max(s1 - s0, 1e-12)))
-            if kind == "cosine":
-                val = v1 + (v0 - v1) * 0.5 * (1.0 + math.cos(math.pi * frac))
-            elif kind == "exponential":
-                val = v0 * (v1 / v0) ** frac if v0 > 0 and v1 > 0 else v0 + (v1 - v0) * frac
-            else:
-                val = v0 + (v1 - v0) * frac
-            self.set_hyperparameter(param, val)
+            s0 = position_to_env_steps(getattr(cfg, f"{param}_schedule_start", None), param=param, default_to_max=False,
+                                       max_env_steps=cfg.max_env_steps)
+            s1 = position_to_env_steps(getattr(cfg, f"{param}_schedule_end", None), param=param, default_to_max=True,
+                                       max_env_steps=cfg.max_env_steps)
+            frac = progress_fraction(float(steps), s0, s1)
+            warm = float(getattr(cfg, f"{param}_schedule_warmup", 0.0) or 0.0)
+            self.set_hyperparameter(param, scheduled_value(kind, float(v0), float(v1), frac, warm))
 
     # ------------------------------------------------------------------------------------------------ fit loop
     def learn(self, *, log_fn=None, max_epochs: Optional[int] = None) -> Dict[str, Any]:

@@ -314,9 +314,78 @@ def golden_wrappers():
     np.savez(os.path.join(OUT, "wrappers.npz"), **out)
 
 
+def golden_host_logic():
+    """Host-side helpers of the path, executed from the reference: schedule interpolation + warm-up + position resolution
+    (trainer_callbacks/hyperparameter_scheduler.py, utils/schedule_resolver.py), RunningStats / RollingWindow
+    (utils/rollout_stats.py) and the resolved hyper-parameters of the three target YAML configs (utils/config.py::load_config)."""
+    # trainer_callbacks/__init__.py imports every callback (watchdog, wandb video, ...): load the one module by path instead
+    import importlib.util
+    pkg = types.ModuleType("trainer_callbacks")
+    pkg.__path__ = [os.path.join(REF, "trainer_callbacks")]
+    sys.modules["trainer_callbacks"] = pkg
+    spec = importlib.util.spec_from_file_location("trainer_callbacks.hyperparameter_scheduler",
+                                                  os.path.join(REF, "trainer_callbacks", "hyperparameter_scheduler.py"))
+    hs = importlib.util.module_from_spec(spec)
+    sys.modules["trainer_callbacks.hyperparameter_scheduler"] = hs
+    spec.loader.exec_module(hs)
+    HyperparameterSchedulerCallback = hs.HyperparameterSchedulerCallback
+    from utils.rollout_stats import RollingWindow, RunningStats
+    from utils.schedule_resolver import schedule_pos_to_vec_steps
+
+    out = {"schedules": [], "positions": [], "running_stats": [], "rolling_window": [], "configs": {}}
+    n_envs, max_env_steps = 8, 100000
+    for kind in ("linear", "cosine", "exponential"):
+        for warm in (0.0, 0.25):
+            for (v0, v1, p0, p1) in ((3e-4, 0.0, 0.0, 1.0), (0.2, 0.05, 0.1, 0.6), (0.0, 0.01, 20000, 60000)):
+                s0 = schedule_pos_to_vec_steps(p0, param="x", default_to_max=False, max_env_steps=max_env_steps, n_envs=n_envs)
+                s1 = schedule_pos_to_vec_steps(p1, param="x", default_to_max=True, max_env_steps=max_env_steps, n_envs=n_envs)
+                got = []
+                cb = HyperparameterSchedulerCallback(schedule=kind, parameter="x", start_value=v0, end_value=v1, start_step=s0, end_step=s1,
+                                                     warmup_fraction=warm, set_value_fn=lambda m, v: got.append(v))
+                steps = [0, 1000, 9999, 10000, 20000, 25000, 33333, 50000, 60000, 75000, 100000, 120000]
+                for env_steps in steps:
+                    mod = SimpleNamespace(get_rollout_collector=lambda stage, e=env_steps: SimpleNamespace(total_vec_steps=e / n_envs))
+                    cb.on_train_epoch_end(None, mod)
+                out["schedules"].append(dict(kind=kind, warmup=warm, start_value=v0, end_value=v1, start=p0, end=p1, env_steps=steps, values=got))
+    for raw in (None, 0.0, 0.3, 1.0, 5000.0):
+        for dflt in (False, True):
+            out["positions"].append(dict(raw=raw, default_to_max=dflt,
+                                         vec_steps=schedule_pos_to_vec_steps(raw, param="x", default_to_max=dflt, max_env_steps=max_env_steps, n_envs=n_envs)))
+    rng = np.random.default_rng(0)
+    rs, seq = RunningStats(), []
+    for shape in ((7,), (3, 4), (0,), (128, 2)):
+        v = (rng.standard_normal(shape) * 3 + 1).astype(np.float64 if len(shape) == 2 else np.float32)
+        rs.update(v)
+        seq.append(dict(values=v.ravel().tolist(), shape=list(shape), dtype=str(v.dtype), count=rs.count, mean=rs.mean(), std=rs.std()))
+    out["running_stats"] = seq
+    rw, means = RollingWindow(5), []
+    vals = rng.standard_normal(12).tolist()
+    for x in vals:
+        rw.append(x)
+        means.append(rw.mean())
+    out["rolling_window"] = dict(maxlen=5, values=vals, means=means, final_len=len(rw))
+    from utils.config import load_config
+    keys = ["env_id", "algo_id", "n_envs", "n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "clip_range", "clip_range_vf", "vf_coef",
+            "ent_coef", "max_grad_norm", "policy_lr", "max_env_steps", "normalize_advantages", "returns_type", "advantages_type", "hidden_dims",
+            "activation", "optimizer", "seed", "eval_episodes", "eval_freq_epochs", "env_wrappers", "target_kl", "model_id", "max_episode_steps"]
+    for env_id, variant in (("CartPole-v1", "ppo"), ("Acrobot-v1", "ppo"), ("MountainCar-v0", "ppo")):
+        cfg = load_config(env_id, variant)
+        row = {}
+        for k in keys:
+            v = getattr(cfg, k, "<absent>")
+            row[k] = list(v) if isinstance(v, tuple) else v
+        if env_id == "MountainCar-v0":
+            row["n_envs"] = "<cpu_count>"        # n_envs "auto" resolves to os.cpu_count() (machine dependent)
+        out["configs"][f"{env_id}:{variant}"] = row
+    with open(os.path.join(OUT, "host_logic.json"), "w") as f:
+        json.dump(out, f, indent=1, default=lambda o: o if isinstance(o, (int, float, str, type(None))) else str(o))
+    print("host logic: schedules", len(out["schedules"]), "configs", list(out["configs"]))
+
+
 if __name__ == "__main__":
     _install_shims()
     golden_wrappers()
+    golden_host_logic()
     golden_returns()
     golden_buffer()
     golden_masked_categorical()
