@@ -377,6 +377,14 @@ def golden_host_logic():
         if env_id == "MountainCar-v0":
             row["n_envs"] = "<cpu_count>"        # n_envs "auto" resolves to os.cpu_count() (machine dependent)
         out["configs"][f"{env_id}:{variant}"] = row
+    # MultiPassRandomSampler (utils/samplers.py:7-37): index stream of 3 passes over 37 items from a seeded generator, then after set_epoch
+    from utils.samplers import MultiPassRandomSampler
+    torch.manual_seed(1234)
+    g = torch.Generator().manual_seed(42)
+    smp = MultiPassRandomSampler(37, 3, generator=g)
+    first = list(smp)
+    smp.set_epoch(5)
+    out["sampler"] = dict(data_len=37, num_passes=3, torch_seed=1234, generator_seed=42, first=first, after_set_epoch_5=list(smp), length=len(smp))
     with open(os.path.join(OUT, "host_logic.json"), "w") as f:
         json.dump(out, f, indent=1, default=lambda o: o if isinstance(o, (int, float, str, type(None))) else str(o))
     print("host logic: schedules", len(out["schedules"]), "configs", list(out["configs"]))
