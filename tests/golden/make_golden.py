@@ -314,6 +314,32 @@ def golden_wrappers():
     np.savez(os.path.join(OUT, "wrappers.npz"), **out)
 
 
+def golden_model_init():
+    """MLPActorCritic / MLPPolicy as the reference constructs and initialises them (utils/models.py:233-346 + utils/torch.py:204-258
+    orthogonal init) from torch.manual_seed(seed): every parameter tensor, plus the forward outputs on a fixed observation batch."""
+    from utils.models import MLPActorCritic, MLPPolicy
+
+    out = {}
+    cases = [("ac_relu_64x64", MLPActorCritic, (4,), (64, 64), (2,), "relu", 0), ("ac_tanh_128x128", MLPActorCritic, (6,), (128, 128), (3,), "tanh", 1),
+             ("ac_relu_64", MLPActorCritic, (2,), (64,), (3,), "relu", 2), ("ac_relu_256x256", MLPActorCritic, (4,), (256, 256), (2,), "relu", 3),
+             ("pol_relu_64x64", MLPPolicy, (4,), (64, 64), (2,), "relu", 4)]
+    for tag, cls, ishape, hidden, oshape, act, seed in cases:
+        torch.manual_seed(seed)
+        m = cls(input_shape=ishape, hidden_dims=hidden, output_shape=oshape, activation=act)
+        for k, v in m.state_dict().items():
+            out[f"{tag}/{k}"] = v.numpy().copy()
+        x = torch.linspace(-1, 1, 5 * ishape[0]).reshape(5, ishape[0])
+        res = m(x)
+        dist, value = res if isinstance(res, tuple) else (res, None)
+        out[f"{tag}/_logits"] = dist.logits.detach().numpy()
+        if value is not None:
+            out[f"{tag}/_value"] = value.detach().numpy()
+        out[f"{tag}/_x"] = x.numpy()
+        out[f"{tag}/_meta"] = np.array(json.dumps(dict(cls=cls.__name__, input_shape=ishape, hidden_dims=hidden, output_shape=oshape, activation=act, seed=seed)))
+    np.savez(os.path.join(OUT, "model_init.npz"), **out)
+    print("model init:", [c[0] for c in cases])
+
+
 def golden_host_logic():
     """Host-side helpers of the path, executed from the reference: schedule interpolation + warm-up + position resolution
     (trainer_callbacks/hyperparameter_scheduler.py, utils/schedule_resolver.py), RunningStats / RollingWindow
@@ -393,6 +419,7 @@ def golden_host_logic():
 if __name__ == "__main__":
     _install_shims()
     golden_wrappers()
+    golden_model_init()
     golden_host_logic()
     golden_returns()
     golden_buffer()
