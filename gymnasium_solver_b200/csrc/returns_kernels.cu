@@ -205,15 +205,42 @@ __global__ void moments_kernel(const float* __restrict__ x, const int32_t* __res
     __shared__ double scratch[32];
     double s = 0.0, s2 = 0.0, c = 0.0;
     const int64_t total = N * (int64_t)T;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        bool use = true;
-        if (last_terminal) {
-            const int64_t t = i / N, n = i - t * N;
-            use = t <= last_terminal[n];
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (!last_terminal && (((uintptr_t)x) & 15) == 0) {
+        // unmasked: 16-byte streaming loads, two in flight per thread (a 4-byte load per iteration left the kernel latency-bound
+        // at ~1.2 TB/s); fp64 accumulation as before
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int64_t n4 = total >> 2;
+        int64_t i = tid0;
+        for (; i + stride < n4; i += 2 * stride) {
+            const float4 a = __ldcs(x4 + i), b = __ldcs(x4 + i + stride);
+            const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w, b0 = b.x, b1 = b.y, b2 = b.z, b3 = b.w;
+            s += ((a0 + a1) + (a2 + a3)) + ((b0 + b1) + (b2 + b3));
+            s2 += ((a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3)) + ((b0 * b0 + b1 * b1) + (b2 * b2 + b3 * b3));
+            c += 8.0;
         }
-        if (use) {
-            const double v = (double)ldg_stream(x + i);
+        for (; i < n4; i += stride) {
+            const float4 a = __ldcs(x4 + i);
+            const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w;
+            s += (a0 + a1) + (a2 + a3);
+            s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            c += 4.0;
+        }
+        for (int64_t j = (n4 << 2) + tid0; j < total; j += stride) {
+            const double v = (double)ldg_stream(x + j);
             s += v; s2 += v * v; c += 1.0;
+        }
+    } else {
+        for (int64_t i = tid0; i < total; i += stride) {
+            bool use = true;
+            if (last_terminal) {
+                const int64_t t = i / N, n = i - t * N;
+                use = t <= last_terminal[n];
+            }
+            if (use) {
+                const double v = (double)ldg_stream(x + i);
+                s += v; s2 += v * v; c += 1.0;
+            }
         }
     }
     s = block_sum(s, scratch);
