@@ -143,3 +143,37 @@ def test_device_reward_wrappers_match_fixtures_generated_by_the_reference_wrappe
         got.append(float(r[0])); dones.append(bool(te[0] or tr[0]))
     np.testing.assert_array_equal(np.array(dones), d[f"{tag}_done"])
     np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"].astype(np.float32), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["mcar_count", "mcar_shaper", "cartpole_shaper"])
+def test_env_surface_with_registry_wrappers_matches_reference_fixture(golden_dir, tag):
+    """The reference-facing surface end to end: build_env(env_id, env_wrappers=[YAML spec]) -> EnvWrapperRegistry.apply ->
+    DeviceVecEnv.reset()/step() (Gymnasium vector protocol: 5-tuple, infos["episode"] / ["_episode"]) against the rewards the
+    reference's wrapper classes produced on the same trajectory (tests/golden/wrappers.npz)."""
+    import json
+    import os
+
+    import torch
+
+    from gymnasium_solver_b200.utils.environment import build_env
+
+    d = np.load(os.path.join(golden_dir, "wrappers.npz"))
+    spec = json.loads(str(d[f"{tag}_kwargs"]))
+    env_id = "CartPole-v1" if tag.startswith("cartpole") else "MountainCar-v0"
+    env = build_env(env_id, n_envs=1, seed=int(d[f"{tag}_seed"]), max_episode_steps=int(d[f"{tag}_max_steps"]), env_wrappers=[spec])
+    assert env.num_envs == 1 and env.wrappers and env.wrappers[0]["id"] == spec["id"]
+    obs, info = env.reset()
+    assert obs.shape == (1, env.single_observation_space.shape[0]) and isinstance(info, dict)
+    got, n_done, ep_len = [], 0, 0
+    for a in d[f"{tag}_actions"]:
+        obs, r, term, trunc, infos = env.step(torch.tensor([int(a)], dtype=torch.int32, device=env.device))
+        got.append(float(r[0]))
+        ep_len += 1
+        if bool(term[0] | trunc[0]):
+            n_done += 1
+            assert bool(infos["_episode"][0]) and int(infos["episode"]["l"][0]) == ep_len
+            ep_len = -1                      # the autoreset step that follows is not part of any episode
+    assert n_done == int(d[f"{tag}_done"].sum())
+    np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"].astype(np.float32), rtol=1e-6, atol=1e-6)
+    with pytest.raises(KeyError):
+        build_env(env_id, n_envs=1, env_wrappers=[{"id": "NoSuchWrapper"}])
