@@ -403,6 +403,19 @@ def golden_host_logic():
         if env_id == "MountainCar-v0":
             row["n_envs"] = "<cpu_count>"        # n_envs "auto" resolves to os.cpu_count() (machine dependent)
         out["configs"][f"{env_id}:{variant}"] = row
+    # utils/torch.py:97-119, 177-190: batch_normalize (unbiased std + 1e-8), KL diagnostics (log-ratio clamped to +-20), group grad norm
+    from utils import torch as ref_torch
+    tg = torch.Generator().manual_seed(9)
+    xs = torch.randn(257, generator=tg) * 3 + 0.5
+    old_lp = -torch.rand(64, generator=tg) * 2
+    new_lp = old_lp + torch.randn(64, generator=tg) * 0.3
+    new_lp[0], new_lp[1] = old_lp[0] + 25.0, old_lp[1] - 30.0           # beyond the clamp
+    kl, akl = ref_torch.compute_kl_diagnostics(old_lp, new_lp)
+    ps = [torch.nn.Parameter(torch.randn(5, 3, generator=tg)), torch.nn.Parameter(torch.randn(7, generator=tg)), torch.nn.Parameter(torch.zeros(2))]
+    ps[0].grad, ps[1].grad = torch.randn(5, 3, generator=tg), torch.randn(7, generator=tg)
+    out["torch_utils"] = dict(x=xs.tolist(), x_normalized=ref_torch.batch_normalize(xs).tolist(), old_logp=old_lp.tolist(), new_logp=new_lp.tolist(),
+                              kl=float(kl), approx_kl=float(akl), grads=[ps[0].grad.reshape(-1).tolist(), ps[1].grad.tolist()],
+                              grad_norm=ref_torch.compute_param_group_grad_norm(ps), grad_norm_none=ref_torch.compute_param_group_grad_norm([ps[2]]))
     # MultiPassRandomSampler (utils/samplers.py:7-37): index stream of 3 passes over 37 items from a seeded generator, then after set_epoch
     from utils.samplers import MultiPassRandomSampler
     torch.manual_seed(1234)
