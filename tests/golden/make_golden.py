@@ -424,6 +424,14 @@ def golden_host_logic():
     first = list(smp)
     smp.set_epoch(5)
     out["sampler"] = dict(data_len=37, num_passes=3, torch_seed=1234, generator_seed=42, first=first, after_set_epoch_5=list(smp), length=len(smp))
+    # the `spec:` blocks of the three target YAML files: the reference's own statement of each env's spaces, rewards and returns
+    import yaml
+    out["env_specs"] = {}
+    for env_id in ("CartPole-v1", "Acrobot-v1", "MountainCar-v0"):
+        doc = yaml.safe_load(open(os.path.join(REF, "config", "environments", f"{env_id}.yaml")))
+        sp = doc["spec"]
+        out["env_specs"][env_id] = dict(action_space=sp["action_space"], observation_state=sp["observation_space"]["variants"]["state"],
+                                        rewards=sp["rewards"], returns=sp["returns"])
     with open(os.path.join(OUT, "host_logic.json"), "w") as f:
         json.dump(out, f, indent=1, default=lambda o: o if isinstance(o, (int, float, str, type(None))) else str(o))
     print("host logic: schedules", len(out["schedules"]), "configs", list(out["configs"]))

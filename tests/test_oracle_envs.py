@@ -204,3 +204,60 @@ def test_reward_wrappers_match_fixtures_generated_by_the_reference_wrappers(gold
     np.testing.assert_array_equal(np.array(dones), d[f"{tag}_done"])
     assert not np.allclose(d[f"{tag}_reward"], d[f"{tag}_base_reward"])          # the wrapper did something
     np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Acrobot-v1", "MountainCar-v0"])
+def test_envs_satisfy_the_reference_yaml_spec_blocks(golden_dir, env_id):
+    """The physics itself is unpinned (gymnasium is not vendored), but the reference states each env's spaces, per-step reward,
+    return range and action meanings in the `spec:` block of its YAML (config/environments/<env>.yaml, extracted into
+    tests/golden/host_logic.json["env_specs"]).  The restatement must satisfy every one of those statements."""
+    import json
+
+    spec = json.load(open(os.path.join(golden_dir, "host_logic.json")))["env_specs"][env_id]
+    n, steps = 64, 1200
+    env = E.OracleVecEnv(env_id, n, seed=5)
+    obs, _ = env.reset()
+    assert env.single_action_space.n == spec["action_space"]["discrete"]
+    assert list(obs.shape[1:]) == spec["observation_state"]["shape"] and str(obs.dtype) == spec["observation_state"]["dtype"]
+    lo = np.array([float(c["range"][0]) for c in spec["observation_state"]["components"]])
+    hi = np.array([float(c["range"][1]) for c in spec["observation_state"]["components"]])
+    rng = np.random.default_rng(0)
+    per_step, prev_done = float(spec["rewards"]["per_step"]), np.zeros(n, bool)
+    ep_returns, ep_lengths = [], []
+    for t in range(steps):
+        obs, r, te, tr, info = env.step(rng.integers(0, env.single_action_space.n, n).astype(np.int32))
+        assert (obs >= lo - 1e-6).all() and (obs <= hi + 1e-6).all()
+        real = ~prev_done                                     # the step after a done is the autoreset step: reward 0, no flags
+        if env_id == "Acrobot-v1":
+            assert np.isin(r[real], (per_step, 0.0)).all() and (r[real & ~te] == per_step).all()      # 0 only on the terminating step
+        else:
+            assert (r[real] == per_step).all()
+        assert (r[~real] == 0).all() and not (te | tr)[~real].any()
+        done = te | tr
+        if done.any():
+            ep_returns += info["episode"]["r"][done].tolist()
+            ep_lengths += info["episode"]["l"][done].tolist()
+        prev_done = done
+    assert len(ep_returns) > n
+    rr = spec["returns"].get("range") or spec["rewards"]["range"]                # Acrobot states the return range under rewards
+    assert min(ep_returns) >= rr[0] and max(ep_returns) <= rr[1]
+    assert max(ep_lengths) <= max(abs(rr[0]), abs(rr[1]))                         # TimeLimit: 500 / 500 / 200 steps
+    if env_id != "CartPole-v1":
+        assert max(ep_lengths) == max(abs(rr[0]), abs(rr[1]))                     # random play runs into the time limit
+    # action labels: the direction each action pushes
+    labels = spec["action_space"]["labels"]
+    one = E.OracleVecEnv(env_id, 1, seed=1)
+    one.reset()
+    s0, e0 = one.get_state()
+    vel_index = {"CartPole-v1": 1, "MountainCar-v0": 1, "Acrobot-v1": 5}[env_id]
+    after = {}
+    for a in range(env.single_action_space.n):
+        one.set_state(s0, e0)
+        o, *_ = one.step(np.array([a], dtype=np.int32))
+        after[a] = float(o[0, vel_index])
+    neg = [int(k) for k, v in labels.items() if v in ("push_left", "torque_negative")][0]
+    pos = [int(k) for k, v in labels.items() if v in ("push_right", "torque_positive")][0]
+    assert after[neg] < after[pos]
+    mid = [int(k) for k, v in labels.items() if v in ("no_push", "torque_zero")]
+    if mid:
+        assert after[neg] < after[mid[0]] < after[pos]
