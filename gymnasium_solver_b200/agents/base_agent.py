@@ -106,6 +106,16 @@ class MetricsRecorder:
             self._host[stage] = {}
         return out
 
+    # names the reference's callbacks call (utils/metrics_recorder.py)
+    def reset_epoch(self, stage: str) -> None:
+        self._host[stage] = {}
+
+    def compute_epoch_means(self, stage: str) -> Dict[str, float]:
+        return self.epoch_means(stage, reset=False)
+
+    def update_history(self, metrics: Dict[str, Any]) -> None:
+        self.history.append(dict(metrics))
+
 
 class BaseAgent(nn.Module):
     def __init__(self, config, *, device=None, rank: Optional[int] = None, world_size: Optional[int] = None):
@@ -584,6 +594,48 @@ class BaseAgent(nn.Module):
         self._early_stop_reason = reason
         return {"history": history, "stop_reason": reason, "epochs": self.current_epoch, "elapsed_s": time.time() - t0,
                 "total_env_steps": col.total_steps * self.world_size, "best_eval_reward": self.best_eval_reward}
+
+    # ------------------------------------------------------------------------------------------------ trainer-shell hooks
+    _fit_t0 = 0.0
+    trainer = None
+
+    def on_fit_start(self) -> None:
+        self._fit_t0 = time.time()
+
+    def on_train_epoch_start(self) -> bool:
+        """reference agents/base_agent.py:284-328: env-step budget check, then collect this epoch's rollout.  False = stop."""
+        cfg, col = self.config, self.get_rollout_collector("train")
+        if cfg.max_env_steps is not None:
+            cur, nxt = col.total_steps * self.world_size, int(cfg.n_envs) * int(cfg.n_steps)
+            if cur + nxt > cfg.max_env_steps:
+                self.set_early_stop_reason(f"'train/cnt/total_env_steps': {cur} + {nxt} would exceed {int(cfg.max_env_steps)}.")
+                return False
+        self._trajectories = col.collect()
+        return True
+
+    def validation_epoch(self) -> Dict[str, Any]:
+        """reference agents/base_agent.py:377-468 (synchronous evaluation): metrics recorded under "val" for the dispatch callback."""
+        ev = self.evaluate("val")
+        self.metrics_recorder.record("val", {k: v for k, v in ev.items() if isinstance(v, (int, float))})
+        mean = ev.get("roll/ep_rew/mean")
+        if mean is not None:
+            self.best_eval_reward = max(self.best_eval_reward, mean)
+        return ev
+
+    def log_dict(self, metrics: Dict[str, Any]) -> None:
+        if self.trainer is not None:
+            self.trainer.log_dict(metrics)
+        self.metrics_recorder.update_history(metrics)
+
+    def set_early_stop_reason(self, reason: str) -> None:
+        self._early_stop_reason = reason
+
+    def fit(self, *, checkpoint_dir=None, callbacks=None, loggers=(), max_epochs: Optional[int] = None) -> Dict[str, Any]:
+        """``learn()`` through the trainer shell (gymnasium_solver_b200/trainer.py): the reference's callback protocol."""
+        from ..trainer import Trainer, build_callbacks
+
+        cbs = list(callbacks) if callbacks is not None else build_callbacks(self, checkpoint_dir=checkpoint_dir)
+        return Trainer(callbacks=cbs, loggers=loggers, max_epochs=max_epochs).fit(self)
 
     def evaluate(self, stage: str = "val") -> Dict[str, Any]:
         col = self.get_rollout_collector(stage)

@@ -322,3 +322,40 @@ def test_checkpoint_resume_continues_bit_for_bit(tmp_path, env, variant, over):
     other = build_agent(_cfg(env, variant, **{**over, "n_envs": over["n_envs"] * 2}), rank=0, world_size=1)
     with pytest.raises(ValueError, match="does not fit"):
         other.get_env("train").restore(sa)
+
+
+def test_fit_through_the_trainer_shell_equals_learn(tmp_path):
+    """the reference's callback protocol (gymnasium_solver_b200/trainer.py: DispatchMetrics -> scheduler -> EarlyStopping
+    -> ModelCheckpoint in callback_builder.py's order) drives the same run as the built-in learn() loop: same epochs, bit-identical
+    weights; metrics arrive under the reference's keys, checkpoints under epoch=NN with last / best links."""
+    import os
+
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.trainer import CsvMetricsLogger
+
+    def make():
+        cfg = _cfg(n_envs=32, n_steps=32, batch_size=256, n_epochs=3, model_id="mlp_64x64", max_env_steps=32 * 32 * 9, eval_freq_epochs=3,
+                   eval_episodes=16, early_stop_on_eval_threshold=False, policy_lr=1e-3, policy_lr_schedule="cosine",
+                   policy_lr_schedule_start_value=1e-3, policy_lr_schedule_end_value=1e-4, policy_lr_schedule_start=0.0, policy_lr_schedule_end=1.0)
+        return build_agent(cfg, rank=0, world_size=1)
+
+    a, b = make(), make()
+    assert a.config.policy_lr_schedule == "cosine"
+    out_a = a.learn()
+    csv_path = tmp_path / "metrics.csv"
+    out_b = b.fit(checkpoint_dir=tmp_path / "ck", loggers=[CsvMetricsLogger(csv_path)])
+    assert out_a["epochs"] == out_b["epochs"] == 9 and out_a["total_env_steps"] == out_b["total_env_steps"] == 32 * 32 * 9
+    assert "would exceed" in out_b["stop_reason"]
+    assert torch.equal(a.policy_model.flat_params, b.policy_model.flat_params)
+    assert a.optimizers().param_groups[0]["lr"] == b.optimizers().param_groups[0]["lr"] < 1e-3
+    lm = b.trainer.logged_metrics
+    for k in ("train/opt/loss/total", "train/opt/ppo/approx_kl", "train/roll/ep_rew/mean", "train/cnt/total_env_steps", "train/sys/timing/fps",
+              "train/progress", "train/cnt/epoch", "val/roll/ep_rew/mean", "val/cnt/epoch"):
+        assert k in lm, k
+    assert lm["train/progress"] == 1.0 and lm["train/cnt/total_env_steps"] == 32 * 32 * 9
+    # three validation epochs (epochs 2, 5, 8): the first always saves and is best; later ones only when better
+    ck = tmp_path / "ck"
+    assert (ck / "epoch=02" / "model.pt").exists() and (ck / "epoch=02" / "env_state.rank0.pt").exists()
+    assert os.readlink(ck / "last").startswith("epoch=") and os.readlink(ck / "best").startswith("epoch=")
+    header = csv_path.read_text().splitlines()[0].split(",")
+    assert "train/opt/loss/total" in header and "val/roll/ep_rew/mean" in header
