@@ -616,7 +616,13 @@ class BaseAgent(nn.Module):
     def validation_epoch(self) -> Dict[str, Any]:
         """reference agents/base_agent.py:377-468 (synchronous evaluation): metrics recorded under "val" for the dispatch callback."""
         ev = self.evaluate("val")
-        self.metrics_recorder.record("val", {k: v for k, v in ev.items() if isinstance(v, (int, float))})
+        scalars = {}
+        for k, v in ev.items():
+            try:
+                scalars[k] = float(v)              # numpy / torch scalars included; arrays and dicts are not loggable
+            except (TypeError, ValueError):
+                pass
+        self.metrics_recorder.record("val", scalars)
         mean = ev.get("roll/ep_rew/mean")
         if mean is not None:
             self.best_eval_reward = max(self.best_eval_reward, mean)

@@ -335,7 +335,7 @@ def test_fit_through_the_trainer_shell_equals_learn(tmp_path):
 
     def make():
         cfg = _cfg(n_envs=32, n_steps=32, batch_size=256, n_epochs=3, model_id="mlp_64x64", max_env_steps=32 * 32 * 9, eval_freq_epochs=3,
-                   eval_episodes=16, early_stop_on_eval_threshold=False, policy_lr=1e-3, policy_lr_schedule="cosine",
+                   eval_episodes=16, eval_warmup_epochs=0, early_stop_on_eval_threshold=False, policy_lr=1e-3, policy_lr_schedule="cosine",
                    policy_lr_schedule_start_value=1e-3, policy_lr_schedule_end_value=1e-4, policy_lr_schedule_start=0.0, policy_lr_schedule_end=1.0)
         return build_agent(cfg, rank=0, world_size=1)
 
