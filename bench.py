@@ -276,10 +276,11 @@ def kernel_rooflines(agent, cfg, dev):
     t = timed(one_update)
     flops = FLOP_PER_SAMPLE_PASS.get(hd, 27264) * agent.local_batch_size
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("update_tc_kernel" if tensor_path else "update_kernel", {}).get("dram_bytes_per_launch")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures
+    traffic_table = json.load(open(tp)) if os.path.exists(tp) else {}
+    full_size = (int(cfg.n_steps), agent.local_n_envs, agent.local_batch_size) == (128, 65536, 1048576)   # the captures' launch sizes
+    tr = lambda name: traffic_table.get(name, {}).get("dram_bytes_per_launch") if full_size else None
+    traffic = tr("update_tc_kernel" if tensor_path else "update_kernel")
     if tensor_path:
         # 144 tcgen05.mma (K=8 tf32) per 128-sample tile; two issuing warps sustain one MMA per ~33 cycles (probes/tc_rate.cu)
         tiles_per_sm = -(-(agent.local_batch_size // 128) // 148)
@@ -314,7 +315,7 @@ def kernel_rooflines(agent, cfg, dev):
     t = timed(one_gae)
     gbytes = GAE_BYTES_PER_ELEM * T * n
     out["gae"] = {"kernel": "gae_kernel<HAS_BOOT>", "bound": "hbm", "achieved": gbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": gbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": gbytes, "avg_launch_s": t}
+                  "frac": gbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": tr("gae_kernel"), "algorithmic_bytes_per_launch": gbytes, "avg_launch_s": t}
 
     # fused collect kernel: 34 B/sample store traffic is the algorithmic HBM figure; it is compute (fp32 MLP + fp64 physics) bound
     def one_collect():
@@ -323,7 +324,7 @@ def kernel_rooflines(agent, cfg, dev):
     t = timed(one_collect, reps=5)
     cbytes = (34 + 12) * T * n
     out["collect"] = {"kernel": "collect_kernel<64,64,64,CartPole> + GAE + stats", "bound": "hbm", "achieved": cbytes / t / 1e9,
-                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": tr("collect_kernel"),
                       "env_steps_per_s": T * n / t, "avg_call_s": t,
                       "note": "whole RolloutCollector.collect() call (collect kernel + GAE + moments); compute-bound, reported for reference"}
     return out
