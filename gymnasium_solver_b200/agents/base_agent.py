@@ -24,6 +24,7 @@ import json
 import math
 import os
 import sys
+import threading
 import time
 from pathlib import Path
 from typing import Any, Dict, Optional
@@ -136,6 +137,18 @@ class BaseAgent(nn.Module):
         self.current_epoch = 0
         self.should_stop = False
         self.best_eval_reward = -float("inf")
+        # asynchronous evaluation (reference agents/base_agent.py:38-40, 65-70)
+        self._eval_models: Dict[str, Any] = {}
+        self._async_eval_thread: Optional[threading.Thread] = None
+        self._async_eval_metrics: Dict[str, Any] = {}
+        self._async_eval_lock = threading.Lock()
+        self._async_eval_shutdown = threading.Event()
+        self._async_eval_pending_epoch: Optional[int] = None
+        self._async_eval_running_epoch: Optional[int] = None
+        self._async_eval_error: Optional[BaseException] = None
+        self._eval_stream = None
+        self._eval_snapshot = None          # weights of the epoch to evaluate next, written on the training stream
+        self._eval_snapshot_event = None
 
         # schedulable hyperparameters (reference agents/base_agent.py:72-77)
         self.policy_lr = config.policy_lr
@@ -204,8 +217,17 @@ class BaseAgent(nn.Module):
 
     def build_rollout_collector(self, stage: str):
         kw = self.config.get_rollout_collector_kwargs()
-        # val / test collectors read the SAME parameter storage: evaluation sees the current weights without copies
-        col = RolloutCollector(self.get_env(stage), self.policy_model, store_next_obs=bool(self.config.store_next_obs),
+        # val / test collectors read the SAME parameter storage: evaluation sees the current weights without copies.  With
+        # eval_async the val collector gets its own copy of the network (reference agents/base_agent.py:197-213): the background
+        # evaluation reads a snapshot while the training stream keeps updating the live weights.
+        model = self.policy_model
+        if stage == "val" and bool(getattr(self.config, "eval_async", False)):
+            model = build_policy_from_env_and_config(self.get_env("train"), self.config)
+            model.to(self.device)
+            model.flatten_parameters_()
+            model.flat_params.copy_(self.policy_model.flat_params)
+            self._eval_models[stage] = model
+        col = RolloutCollector(self.get_env(stage), model, store_next_obs=bool(self.config.store_next_obs),
                                rng_seed=_mix64(int(self.config.seed) * 3 + STAGES.index(stage)) >> 1, **kw)
         self._rollout_collectors[stage] = col
         return col
@@ -573,11 +595,11 @@ class BaseAgent(nn.Module):
                     self.should_stop = True
             if cfg.eval_freq_epochs and (self.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
                     and self.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
-                ev = self.evaluate("val")
+                self.metrics_recorder.reset_epoch("val")
+                ev = self.validation_epoch()        # synchronous, or the latest finished background evaluation (eval_async)
                 row.update({f"val/{k}": v for k, v in ev.items()})
                 mean = ev.get("roll/ep_rew/mean")
                 if mean is not None:
-                    self.best_eval_reward = max(self.best_eval_reward, mean)
                     thr = cfg.early_stop_on_eval_threshold
                     if thr:
                         limit = cfg.reward_threshold if cfg.reward_threshold is not None else self.get_env("val").get_return_threshold()
@@ -592,6 +614,7 @@ class BaseAgent(nn.Module):
             if self.should_stop:
                 break
         self._early_stop_reason = reason
+        self.on_fit_end()
         return {"history": history, "stop_reason": reason, "epochs": self.current_epoch, "elapsed_s": time.time() - t0,
                 "total_env_steps": col.total_steps * self.world_size, "best_eval_reward": self.best_eval_reward}
 
@@ -614,19 +637,117 @@ class BaseAgent(nn.Module):
         return True
 
     def validation_epoch(self) -> Dict[str, Any]:
-        """reference agents/base_agent.py:377-468 (synchronous evaluation): metrics recorded under "val" for the dispatch callback."""
-        ev = self.evaluate("val")
+        """reference agents/base_agent.py:377-496.  Synchronous: evaluate now, record under "val" for the dispatch callback.
+        ``eval_async``: start (or queue) a background evaluation of the current weights and record the most recent finished one,
+        which may belong to an earlier epoch (``eval/model_epoch`` says which)."""
+        if bool(getattr(self.config, "eval_async", False)):
+            self._raise_async_eval_error()
+            self._launch_async_eval()
+            with self._async_eval_lock:
+                ev = dict(self._async_eval_metrics)
+        else:
+            ev = self.evaluate("val")
         scalars = {}
         for k, v in ev.items():
             try:
                 scalars[k] = float(v)              # numpy / torch scalars included; arrays and dicts are not loggable
             except (TypeError, ValueError):
                 pass
-        self.metrics_recorder.record("val", scalars)
+        if scalars:
+            self.metrics_recorder.record("val", scalars)
         mean = ev.get("roll/ep_rew/mean")
         if mean is not None:
             self.best_eval_reward = max(self.best_eval_reward, mean)
         return ev
+
+    # ------------------------------------------------------------------------------------------------ asynchronous evaluation
+    def _launch_async_eval(self, eval_epoch: Optional[int] = None) -> None:
+        """reference agents/base_agent.py:387-463.  Called on the training thread.  The weights of ``eval_epoch`` are snapshotted with
+        one device copy ON THE TRAINING STREAM (ordered after the last optimizer step, no host sync); a daemon thread evaluates
+        the snapshot on its own CUDA stream with the val collector / env / network copy.  While an evaluation is running the
+        newest request is kept as pending (its snapshot replaces an older pending one) and starts when the running one ends."""
+        if self._async_eval_shutdown.is_set():
+            return
+        if "val" not in self._eval_models:
+            raise N.EngineError("eval_async needs the val collector's own network copy: set config.eval_async before constructing the agent")
+        eval_epoch = int(self.current_epoch) if eval_epoch is None else int(eval_epoch)
+        with self._async_eval_lock:
+            # under the lock the eval thread is not reading the snapshot (it copies it out and synchronises under the same lock)
+            if self._eval_snapshot is None:
+                self._eval_snapshot = torch.empty_like(self.policy_model.flat_params)
+                self._eval_snapshot_event = torch.cuda.Event()
+                self._eval_stream = torch.cuda.Stream(device=self.device)
+            self._eval_snapshot.copy_(self.policy_model.flat_params)
+            self._eval_snapshot_event.record()
+            if self._async_eval_thread is not None and self._async_eval_thread.is_alive() and self._async_eval_running_epoch is not None:
+                self._async_eval_pending_epoch = eval_epoch
+                return
+            self._async_eval_running_epoch = eval_epoch
+            self._async_eval_pending_epoch = None
+        self._async_eval_thread = threading.Thread(target=self._run_async_eval, name="gs-async-eval", daemon=True)
+        self._async_eval_thread.start()
+
+    def _run_async_eval(self) -> None:
+        try:
+            with torch.cuda.device(self.device), torch.cuda.stream(self._eval_stream):
+                while not self._async_eval_shutdown.is_set():
+                    with self._async_eval_lock:
+                        epoch = self._async_eval_running_epoch
+                        self._eval_stream.wait_event(self._eval_snapshot_event)
+                        self._eval_models["val"].flat_params.copy_(self._eval_snapshot)
+                        self._eval_stream.synchronize()
+                    t0 = time.time()
+                    metrics = self.evaluate("val")
+                    dt = time.time() - t0
+                    with self._async_eval_lock:
+                        self._async_eval_metrics = {**metrics, "cnt/epoch": int(epoch), "eval/model_epoch": int(epoch),
+                                                    "epoch_fps": metrics.get("cnt/total_vec_steps", 0) / dt if dt > 0 else 0.0}
+                        self._async_eval_running_epoch = self._async_eval_pending_epoch
+                        self._async_eval_pending_epoch = None
+                        if self._async_eval_running_epoch is None:
+                            return
+        except BaseException as e:                      # fail fast: re-raised on the training thread at the next validation epoch
+            with self._async_eval_lock:
+                self._async_eval_error = e
+                self._async_eval_running_epoch = None
+                self._async_eval_pending_epoch = None
+
+    def _raise_async_eval_error(self) -> None:
+        with self._async_eval_lock:
+            err, self._async_eval_error = self._async_eval_error, None
+        if err is not None:
+            raise N.EngineError(f"asynchronous evaluation failed: {err!r}") from err
+
+    def wait_async_eval(self, timeout: Optional[float] = None) -> Dict[str, Any]:
+        """Block until the running (and any pending) background evaluation has finished; returns its metrics."""
+        th = self._async_eval_thread
+        if th is not None:
+            th.join(timeout)
+        self._raise_async_eval_error()
+        with self._async_eval_lock:
+            return dict(self._async_eval_metrics)
+
+    def get_async_eval_metric(self, metric_key: str) -> Optional[float]:
+        """reference agents/base_agent.py:649-652."""
+        with self._async_eval_lock:
+            return self._async_eval_metrics.get(metric_key)
+
+    def _cleanup_async_eval(self) -> None:
+        """reference agents/base_agent.py:498-507 (there the join gives up after 5 s; here a running evaluation is allowed to end, the
+        pending one is dropped)."""
+        if not bool(getattr(self.config, "eval_async", False)):
+            return
+        with self._async_eval_lock:
+            self._async_eval_pending_epoch = None
+        self._async_eval_shutdown.set()
+        th = self._async_eval_thread
+        if th is not None and th.is_alive():
+            th.join()
+        self._async_eval_thread = None
+        self._raise_async_eval_error()
+
+    def on_fit_end(self) -> None:
+        self._cleanup_async_eval()
 
     def log_dict(self, metrics: Dict[str, Any]) -> None:
         if self.trainer is not None:

@@ -78,6 +78,8 @@ class Trainer:
                 agent.validation_epoch()
                 self._call("on_validation_epoch_end", agent)
             agent.current_epoch += 1
+        if hasattr(agent, "on_fit_end"):                     # module hook (Lightning calls it when defined): joins a background evaluation
+            agent.on_fit_end()
         self._call("on_fit_end", agent)
         for lg in self.loggers:
             lg.close()

@@ -9,6 +9,7 @@ bookkeeping is resolved lazily, so ``collect()`` itself never synchronises with 
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import time
 from typing import List, Optional, Tuple
 
@@ -338,6 +339,13 @@ class RolloutCollector:
     @torch.no_grad()
     def evaluate_episodes(self, *, n_episodes: int, deterministic: bool = True, timeout_seconds: Optional[float] = None) -> dict:
         """Exactly-N-episodes evaluation with balanced per-env quotas (reference: rollout_collector.py:569-655)."""
+        self._busy_thread = threading.get_ident()
+        try:
+            return self._evaluate_episodes(n_episodes, deterministic, timeout_seconds)
+        finally:
+            self._busy_thread = None
+
+    def _evaluate_episodes(self, n_episodes: int, deterministic: bool, timeout_seconds: Optional[float]) -> dict:
         n = self.n_envs
         base, rem = int(n_episodes) // n, int(n_episodes) % n
         targets = torch.tensor([base + (1 if i < rem else 0) for i in range(n)], device=self.env.device) if n_episodes > 0 else \
@@ -382,7 +390,15 @@ class RolloutCollector:
             idx = self._last_rollout_index_map[idx]
         return RolloutTrajectory(*(getattr(trajectories, f)[idx] for f in RolloutTrajectory._fields))
 
+    _busy_thread = None           # ident of the thread inside evaluate_episodes()
+    _metrics_snapshot: dict = {}
+
     def get_metrics(self) -> dict:
+        busy = self._busy_thread
+        if busy is not None and busy != threading.get_ident():
+            # an evaluation is running on another thread and stream (BaseAgent eval_async): the collector's buffers are in use there,
+            # so a reader on this thread gets the view of the last completed call instead of touching them
+            return dict(self._metrics_snapshot)
         self._resolve_pending_episodes()
         self._flush_stats()
         if self._events_pending and self._events is not None:
@@ -419,6 +435,7 @@ class RolloutCollector:
             m["roll/ep_rew/best"] = float(self._best_episode_reward)
             m["roll/ep_rew/last"] = float(self._last_episode_reward)
             m["roll/ep_len/last"] = int(self._last_episode_length)
+        self._metrics_snapshot = dict(m)
         return m
 
     _recent_dev = None

@@ -359,3 +359,54 @@ def test_fit_through_the_trainer_shell_equals_learn(tmp_path):
     assert os.readlink(ck / "last").startswith("epoch=") and os.readlink(ck / "best").startswith("epoch=")
     header = csv_path.read_text().splitlines()[0].split(",")
     assert "train/opt/loss/total" in header and "val/roll/ep_rew/mean" in header
+
+
+def test_async_evaluation_beside_training_matches_synchronous_evaluation(tmp_path):
+    """SURVEY 8(f) n2 / reference agents/base_agent.py:204-213, 387-463: with ``eval_async`` the val collector owns a copy of the network
+    and a background thread evaluates a snapshot of the weights on its own CUDA stream while the training stream goes on.  Training is
+    unaffected bit for bit; the first background evaluation equals the synchronous evaluation of the same epoch's weights (same val env
+    seed, deterministic actions); requests made while one is running collapse into one pending evaluation of the newest weights."""
+    from gymnasium_solver_b200.agents import build_agent
+
+    def make(**over):
+        cfg = _cfg(n_envs=32, n_steps=32, batch_size=256, n_epochs=3, model_id="mlp_64x64", eval_episodes=64, eval_warmup_epochs=0,
+                   eval_deterministic=True, early_stop_on_eval_threshold=False, early_stop_on_train_threshold=False, **over)
+        return build_agent(cfg, rank=0, world_size=1)
+
+    sync = make(eval_freq_epochs=6, eval_async=False)
+    out_s = sync.learn(max_epochs=6)
+    ev_s = {k: v for k, v in out_s["history"][-1].items() if k.startswith("val/")}
+    assert ev_s["val/cnt/total_episodes"] == 64
+
+    # (1) one request at the same epoch: same evaluation, same training
+    a = make(eval_freq_epochs=6, eval_async=True)
+    assert a.get_rollout_collector("val").policy_model is not a.policy_model
+    assert a.get_rollout_collector("test").policy_model is a.policy_model
+    a.learn(max_epochs=6)                      # on_fit_end joins the background evaluation
+    assert a._async_eval_thread is None
+    assert torch.equal(a.policy_model.flat_params, sync.policy_model.flat_params)
+    ev_a = a.wait_async_eval()
+    assert ev_a["eval/model_epoch"] == 5 and ev_a["cnt/epoch"] == 5 and ev_a["epoch_fps"] > 0
+    for k in ("roll/ep_rew/mean", "roll/ep_len/mean", "cnt/total_episodes", "cnt/total_env_steps"):
+        assert ev_a[k] == ev_s[f"val/{k}"], k
+    assert a.get_async_eval_metric("roll/ep_rew/mean") == ev_a["roll/ep_rew/mean"]
+    assert torch.equal(a._eval_models["val"].flat_params, a.policy_model.flat_params)      # the snapshot of the last epoch
+
+    # (2) a request every epoch, through the trainer shell: training still bit-identical, evaluations of increasing epochs arrive
+    b = make(eval_freq_epochs=1, eval_async=True)
+    out_b = b.fit(checkpoint_dir=tmp_path / "ck", max_epochs=6)
+    assert out_b["epochs"] == 6 and b._async_eval_thread is None
+    assert torch.equal(b.policy_model.flat_params, sync.policy_model.flat_params)
+    ev_b = b.wait_async_eval()
+    assert 0 <= ev_b["eval/model_epoch"] <= 5 and ev_b["cnt/total_episodes"] == 64
+    epochs_seen = [r["val/eval/model_epoch"] for r in b.metrics_recorder.history if "val/eval/model_epoch" in r]
+    assert epochs_seen == sorted(epochs_seen)
+    # after shutdown no new evaluation starts
+    b._launch_async_eval()
+    assert b._async_eval_thread is None
+
+    # (3) eval_async switched on after construction has no network copy to evaluate: loud error, no silent shared-weights race
+    c = make(eval_freq_epochs=1, eval_async=False)
+    c.config.eval_async = True
+    with pytest.raises(Exception, match="eval_async"):
+        c.validation_epoch()
