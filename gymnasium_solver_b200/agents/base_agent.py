@@ -41,6 +41,7 @@ from ..utils.policy_factory import build_policy_from_env_and_config
 from ..utils.rollout_collector import DeviceTrajectory, RolloutCollector
 from ..utils.rollout_buffer import RolloutTrajectory
 from ..utils.schedules import position_to_env_steps, progress_fraction, scheduled_value
+from ..utils.timings_tracker import TimingsTracker
 
 STAGES = ["train", "val", "test"]
 _SPLITMIX = 0x9E3779B97F4A7C15
@@ -157,6 +158,7 @@ class BaseAgent(nn.Module):
         self.ent_coef = config.ent_coef
         self.n_epochs = config.n_epochs
         self.metrics_recorder = MetricsRecorder()
+        self.timings = TimingsTracker()
 
         self.shard = shard_spec(int(config.n_envs), int(config.batch_size), self.rank, self.world_size)
         self.local_n_envs, self.local_batch_size = self.shard.n_envs, self.shard.batch_size
@@ -357,6 +359,23 @@ class BaseAgent(nn.Module):
         self._metrics_sum += self._metrics_dev
         self._metrics_n += 1
         opt.step()
+
+    def train_dataloader(self):
+        """reference agents/base_agent.py:253-283: collect the first rollout and build the index-collate loader over
+        ``self._trajectories`` (re-read for every minibatch, so the one loader serves every later rollout).  For callers that drive
+        ``training_step(batch, batch_idx)`` themselves the way Lightning drove the reference; ``learn()`` / ``fit()`` do not go through
+        it (their update kernels gather in place).  The local shard's batch size is used: every rank feeds its own loader."""
+        from ..utils.dataloaders import build_index_collate_loader_from_collector
+        from ..utils.random import get_global_torch_generator
+
+        assert self.current_epoch == 0 or getattr(self, "_resume_from_epoch", None) is not None, \
+            "train_dataloader should only be called once at the start of training"
+        col = self.get_rollout_collector("train")
+        self._trajectories = col.collect()
+        self._train_dataloader = build_index_collate_loader_from_collector(
+            collector=col, trajectories_getter=lambda: self._trajectories, batch_size=self.local_batch_size,
+            num_passes=self.config.n_epochs, generator=get_global_torch_generator(self.config.seed))
+        return self._train_dataloader
 
     # ------------------------------------------------------------------------------------------------ one epoch
     def minibatches(self, traj: DeviceTrajectory, epoch_key: int):
@@ -566,6 +585,7 @@ class BaseAgent(nn.Module):
         cfg = self.config
         col = self.get_rollout_collector("train")
         t0 = time.time()
+        self.on_fit_start()
         history = []
         max_epochs = max_epochs if max_epochs is not None else cfg.max_epochs
         reason = ""
@@ -624,10 +644,17 @@ class BaseAgent(nn.Module):
 
     def on_fit_start(self) -> None:
         self._fit_t0 = time.time()
+        self.timings.start("on_fit_start", values=self._host_counters("train"))
+
+    def _host_counters(self, stage: str) -> Dict[str, float]:
+        """The collector's step counters as plain host ints (no device sync, unlike get_metrics()): baselines of the time markers."""
+        col = self.get_rollout_collector(stage)
+        return {"cnt/total_env_steps": col.total_steps, "cnt/total_vec_steps": col.total_vec_steps, "cnt/epoch": self.current_epoch}
 
     def on_train_epoch_start(self) -> bool:
         """reference agents/base_agent.py:284-328: env-step budget check, then collect this epoch's rollout.  False = stop."""
         cfg, col = self.config, self.get_rollout_collector("train")
+        self.timings.start("on_train_epoch_start", values=self._host_counters("train"))
         if cfg.max_env_steps is not None:
             cur, nxt = col.total_steps * self.world_size, int(cfg.n_envs) * int(cfg.n_steps)
             if cur + nxt > cfg.max_env_steps:
@@ -640,6 +667,7 @@ class BaseAgent(nn.Module):
         """reference agents/base_agent.py:377-496.  Synchronous: evaluate now, record under "val" for the dispatch callback.
         ``eval_async``: start (or queue) a background evaluation of the current weights and record the most recent finished one,
         which may belong to an earlier epoch (``eval/model_epoch`` says which)."""
+        self.timings.start("on_validation_epoch_start", values={"cnt/epoch": self.current_epoch})
         if bool(getattr(self.config, "eval_async", False)):
             self._raise_async_eval_error()
             self._launch_async_eval()

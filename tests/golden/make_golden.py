@@ -437,11 +437,41 @@ def golden_host_logic():
     print("host logic: schedules", len(out["schedules"]), "configs", list(out["configs"]))
 
 
+def golden_dataloader():
+    """utils/dataloaders.py:20-77 executed from the reference over a recording collector: which index batches reach
+    ``collector.slice_trajectories`` (n_epochs permutations from a seeded generator, cut into consecutive minibatches), the loader
+    length, and the two ValueErrors (no trajectories; batch size that does not divide the rollout)."""
+    from utils.dataloaders import build_index_collate_loader_from_collector
+
+    class Collector:
+        def slice_trajectories(self, traj, idxs):
+            return [int(i) for i in idxs]
+
+    traj = SimpleNamespace(observations=torch.zeros(48, 4))
+    torch.manual_seed(77)
+    g = torch.Generator().manual_seed(9)
+    loader = build_index_collate_loader_from_collector(collector=Collector(), trajectories=traj, batch_size=16, num_passes=3, generator=g)
+    first = [b for b in loader]
+    second = [b for b in loader]                       # the generator moves on: the next epoch draws new permutations
+    errors = {}
+    for tag, kw in (("indivisible", dict(trajectories=traj, batch_size=10)), ("missing", dict(batch_size=16))):
+        try:
+            build_index_collate_loader_from_collector(collector=Collector(), num_passes=1, **kw)
+        except ValueError as e:
+            errors[tag] = str(e)
+    out = dict(data_len=48, batch_size=16, num_passes=3, torch_seed=77, generator_seed=9, length=len(loader), first=first, second=second,
+               errors=errors)
+    with open(os.path.join(OUT, "dataloader.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("dataloader:", len(first), "batches per epoch;", errors)
+
+
 if __name__ == "__main__":
     _install_shims()
     golden_wrappers()
     golden_model_init()
     golden_host_logic()
+    golden_dataloader()
     golden_returns()
     golden_buffer()
     golden_masked_categorical()

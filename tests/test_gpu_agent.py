@@ -410,3 +410,44 @@ def test_async_evaluation_beside_training_matches_synchronous_evaluation(tmp_pat
     c.config.eval_async = True
     with pytest.raises(Exception, match="eval_async"):
         c.validation_epoch()
+
+
+def test_train_dataloader_drives_training_step_like_lightning():
+    """SURVEY 8a row a12 / reference agents/base_agent.py:253-283, 330-366: the index-collate loader built once over ``_trajectories`` feeds
+    reference-style gathered minibatches (RolloutTrajectory of flat tensors) into ``training_step``; a later rollout is served by the same
+    loader.  Each minibatch's loss equals the oracle's PPO loss of the same gathered batch under the weights of that step."""
+    from gymnasium_solver_b200.agents import build_agent
+    from gymnasium_solver_b200.utils.rollout_buffer import RolloutTrajectory
+
+    cfg = _cfg(n_envs=16, n_steps=32, batch_size=128, n_epochs=2, model_id="mlp_64x64")
+    agent = build_agent(cfg, rank=0, world_size=1)
+    loader = agent.train_dataloader()
+    assert len(loader) == 2 * (16 * 32 // 128) and loader.batch_size == 128
+    with pytest.raises(AssertionError, match="only be called once"):
+        agent.current_epoch = 1
+        agent.train_dataloader()
+    agent.current_epoch = 0
+    w0 = agent.policy_model.flat_params.clone()
+    for epoch in range(2):
+        if epoch == 1:
+            agent._trajectories = agent.get_rollout_collector("train").collect()
+        first_obs = agent._trajectories.observations
+        seen = torch.zeros(16 * 32, dtype=torch.int64)
+        for i, batch in enumerate(loader):
+            assert isinstance(batch, RolloutTrajectory) and batch.observations.shape == (128, 4) and batch.actions.dtype == torch.int64
+            if i == 0:
+                p = _oracle_params(agent.policy_model)
+                want, _ = OP.ppo_loss(p, *(getattr(batch, f).cpu() for f in ("observations", "actions", "logprobs", "values", "advantages", "returns")),
+                                      clip_range=cfg.clip_range, clip_range_vf=cfg.clip_range_vf, vf_coef=cfg.vf_coef, ent_coef=cfg.ent_coef,
+                                      normalize_adv=cfg.normalize_advantages == "batch")
+                got = agent.losses_for_batch(batch, 0)["loss"]
+                np.testing.assert_allclose(float(got.item()), float(want), rtol=1e-4, atol=1e-5)
+            # which rows of the rollout this minibatch holds (observations are unique per sample with probability 1)
+            match = (batch.observations[:, None, :] == first_obs[None, :, :]).all(dim=2)
+            seen += match.any(dim=0).cpu().to(torch.int64)
+            agent.training_step(batch, i)
+        assert i == len(loader) - 1
+        assert int(seen.min()) >= 2                    # two passes: every sample of the rollout was gathered at least twice
+    assert not torch.equal(w0, agent.policy_model.flat_params)
+    m = agent.pop_epoch_metrics()
+    assert np.isfinite(m["opt/loss/total"]) and m["opt/grads/norm/all"] > 0
