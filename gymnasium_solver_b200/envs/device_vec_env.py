@@ -8,6 +8,7 @@ protocol compatibility and for the parity tests.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from types import SimpleNamespace
 
@@ -28,11 +29,19 @@ class _Discrete:
         return int(np.random.randint(self.n))
 
 
+# observation_space.high of the upstream envs (gymnasium 1.1.1 classic_control; low = -high except MountainCar's position).  Stated from
+# the upstream sources like the physics (un-vendored, so unpinned); the reference's YAML `spec:` blocks agree where finite.
+_OBS_HIGH = {"CartPole-v1": [4.8, np.inf, 12 * 2 * np.pi / 360 * 2, np.inf],
+             "Acrobot-v1": [1.0, 1.0, 1.0, 1.0, 4 * np.pi, 9 * np.pi],
+             "MountainCar-v0": [0.6, 0.07]}
+_OBS_LOW = {"MountainCar-v0": [-1.2, -0.07]}
+
+
 class _Box:
-    def __init__(self, shape):
+    def __init__(self, shape, low=None, high=None):
         self.shape, self.dtype = tuple(shape), np.float32
-        self.high = np.full(self.shape, np.inf, dtype=np.float32)
-        self.low = -self.high
+        self.high = np.broadcast_to(np.asarray(np.inf if high is None else high, dtype=np.float32), self.shape).copy()
+        self.low = -self.high if low is None else np.broadcast_to(np.asarray(low, dtype=np.float32), self.shape).copy()
 
 
 class DeviceVecEnv:
@@ -56,9 +65,9 @@ class DeviceVecEnv:
         self.obs_dim = N.lib().gs_env_obs_dim(self.kind)
         self.state_dim = N.lib().gs_env_state_dim(self.kind)
         self.n_actions = N.lib().gs_env_n_actions(self.kind)
-        self.single_observation_space = _Box((self.obs_dim,))
+        self.single_observation_space = _Box((self.obs_dim,), _OBS_LOW.get(env_id), _OBS_HIGH[env_id])
         self.single_action_space = _Discrete(self.n_actions)
-        self.observation_space = _Box((self.num_envs, self.obs_dim))
+        self.observation_space = _Box((self.num_envs, self.obs_dim), _OBS_LOW.get(env_id), _OBS_HIGH[env_id])
         self.action_space = SimpleNamespace(shape=(self.num_envs,), n=self.n_actions)
         self.render_mode = None
         self.spec_dict = dict(spec or {})
@@ -172,3 +181,10 @@ class DeviceVecEnv:
 
     def get_max_episode_steps(self):
         return self.max_episode_steps
+
+    @contextlib.contextmanager
+    def recorder(self, video_path=None, record_video: bool = True, **_):
+        """``with env.recorder(path, record_video=...)`` around an evaluation (reference gym_wrappers/env_video_recorder.py:180).  Device
+        environments have no renderer (``render_mode`` is None), so like the reference's own non-rendering vector adapter
+        (gym_wrappers/ale_vec_env_adapter.py:87-97) this is a no-op context: nothing is written to ``video_path``."""
+        yield self

@@ -177,3 +177,38 @@ def test_env_surface_with_registry_wrappers_matches_reference_fixture(golden_dir
     np.testing.assert_allclose(np.array(got), d[f"{tag}_reward"].astype(np.float32), rtol=1e-6, atol=1e-6)
     with pytest.raises(KeyError):
         build_env(env_id, n_envs=1, env_wrappers=[{"id": "NoSuchWrapper"}])
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Acrobot-v1", "MountainCar-v0"])
+def test_observation_space_bounds_and_recorder_protocol(golden_dir, env_id):
+    """SURVEY 8(b) env protocol: ``single_observation_space`` is a float32 Box whose finite bounds agree with the reference's YAML `spec:`
+    block (config/environments/<env>.yaml, in host_logic.json) and hold along a random trajectory; ``recorder()`` is a context
+    manager (no-op: nothing renders on the device), ``render_mode`` is None, ``unwrapped`` is the env."""
+    import json
+    import os
+
+    from gymnasium_solver_b200.envs.device_vec_env import DeviceVecEnv
+
+    spec = json.load(open(os.path.join(str(golden_dir), "host_logic.json")))["env_specs"][env_id]
+    env = DeviceVecEnv(env_id, 256, seed=3)
+    box = env.single_observation_space
+    comps = spec["observation_state"]["components"]
+    assert box.shape == tuple(spec["observation_state"]["shape"]) and box.dtype == np.float32 and box.low.dtype == np.float32
+    assert env.observation_space.shape == (256,) + box.shape
+    for d, c in enumerate(comps):
+        lo, hi = float(c["range"][0]), float(c["range"][1])
+        if np.isfinite(lo):                    # the YAML rounds (0.418 for 12 degrees * 2 in radians)
+            assert abs(box.low[d] - lo) < 1e-3 and abs(box.high[d] - hi) < 1e-3, (d, box.low[d], box.high[d])
+        assert box.low[d] < box.high[d]
+    obs, _ = env.reset()
+    g = torch.Generator().manual_seed(0)
+    lo_t, hi_t = torch.from_numpy(box.low).cuda(), torch.from_numpy(box.high).cuda()
+    for _ in range(300):
+        # a terminal CartPole observation may leave the Box by one step (the env reports the state that crossed the threshold),
+        # like upstream: bounds are twice the termination thresholds
+        assert bool(((obs >= lo_t) & (obs <= hi_t)).all())
+        obs, *_ = env.step(torch.randint(0, env.n_actions, (256,), generator=g))
+    with env.recorder("unused.mp4", record_video=True) as e:
+        assert e is env
+    assert env.render_mode is None and env.unwrapped is env and not os.path.exists("unused.mp4")
+    env.close()
