@@ -73,21 +73,22 @@ class RolloutBuffer:
         self.size = max(self.size, self.pos)
         return start
 
-    def add(self, idx: int, obs, next_obs, actions, logps, values, rewards, dones, timeouts) -> None:
-        """Per-step write (protocol compatibility; the fused collect kernel writes the same arrays directly)."""
-        obs_t = torch.as_tensor(obs)
+    def add(self, idx: int, obs_np, next_obs_np, actions_np, logps_np, values_np, rewards_np, dones_np, timeouts_np) -> None:
+        """Per-step write, the reference's parameter names (utils/rollout_buffer.py:82-93; its tests pass them by keyword).  Protocol
+        compatibility: the fused collect kernel writes the same arrays directly.  numpy arrays or tensors on any device."""
+        obs_t = torch.as_tensor(obs_np)
         assert tuple(obs_t.shape) == (self.n_envs, *self.obs_shape), \
             f"Expected shape {(self.n_envs, *self.obs_shape)}, got {tuple(obs_t.shape)}"
         put = lambda buf, v: buf[idx].copy_(torch.as_tensor(v).to(buf.dtype))
         put(self.obs_buf, obs_t)
         if self.next_obs_buf is not None:
-            put(self.next_obs_buf, next_obs)
-        put(self.actions_buf, actions)
-        put(self.logprobs_buf, logps)
-        put(self.values_buf, values)
-        put(self.rewards_buf, rewards)
-        put(self.dones_buf, dones)
-        put(self.timeouts_buf, timeouts)
+            put(self.next_obs_buf, next_obs_np)
+        put(self.actions_buf, actions_np)
+        put(self.logprobs_buf, logps_np)
+        put(self.values_buf, values_np)
+        put(self.rewards_buf, rewards_np)
+        put(self.dones_buf, dones_np)
+        put(self.timeouts_buf, timeouts_np)
 
     def flatten_slice_env_major(self, start: int, end: int, advantages_buf, returns_buf) -> RolloutTrajectory:
         """Materialise the reference's env-major (N*T, ...) training tensors for [start, end).
