@@ -187,6 +187,8 @@ def test_observation_space_bounds_and_recorder_protocol(golden_dir, env_id):
     import json
     import os
 
+    import torch
+
     from gymnasium_solver_b200.envs.device_vec_env import DeviceVecEnv
 
     spec = json.load(open(os.path.join(str(golden_dir), "host_logic.json")))["env_specs"][env_id]
