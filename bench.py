@@ -233,7 +233,6 @@ def run_b200(args):
 
 def kernel_rooflines(agent, cfg, dev):
     """Per-kernel achieved rates, each kernel timed alone with CUDA events on the launching stream."""
-    import ctypes as C
     from gymnasium_solver_b200 import _native as N
 
     peaks = _peaks()

@@ -39,7 +39,6 @@ from ..utils.environment import build_env_from_config
 from ..utils.optimizer_factory import EngineAdam, build_optimizer
 from ..utils.policy_factory import build_policy_from_env_and_config
 from ..utils.rollout_collector import DeviceTrajectory, RolloutCollector
-from ..utils.rollout_buffer import RolloutTrajectory
 from ..utils.schedules import position_to_env_steps, progress_fraction, scheduled_value
 from ..utils.timings_tracker import TimingsTracker
 

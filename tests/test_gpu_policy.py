@@ -71,7 +71,6 @@ def test_policy_only_model_returns_zero_values_and_philox_sampling_is_unbiased()
 
 
 def test_unsupported_shapes_fail_loudly():
-    import ctypes as C
     import engine_api as E
     from gymnasium_solver_b200 import _native as N
 

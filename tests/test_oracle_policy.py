@@ -1,6 +1,5 @@
 """Pins oracle/policy.py against fixtures produced by the reference's MLPActorCritic / MLPPolicy / policy_act /
 PPOAgent.losses_for_batch / REINFORCEAgent.losses_for_batch (tests/golden/make_golden.py)."""
-import glob
 import os
 
 import numpy as np

@@ -4,7 +4,6 @@ import glob
 import os
 
 import numpy as np
-import pytest
 
 from oracle import returns as R
 
