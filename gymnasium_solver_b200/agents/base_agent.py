@@ -643,6 +643,7 @@ class BaseAgent(nn.Module):
 
     def on_fit_start(self) -> None:
         self._fit_t0 = time.time()
+        self._async_eval_shutdown.clear()          # a new fit may evaluate in the background again (set by the previous on_fit_end)
         self.timings.start("on_fit_start", values=self._host_counters("train"))
 
     def _host_counters(self, stage: str) -> Dict[str, float]:

@@ -404,6 +404,9 @@ def test_async_evaluation_beside_training_matches_synchronous_evaluation(tmp_pat
     # after shutdown no new evaluation starts
     b._launch_async_eval()
     assert b._async_eval_thread is None
+    # ... until the next fit: one more epoch, evaluated in the background again
+    out_b2 = b.learn(max_epochs=7)
+    assert out_b2["epochs"] == 7 and b.wait_async_eval()["eval/model_epoch"] == 6
 
     # (3) eval_async switched on after construction has no network copy to evaluate: loud error, no silent shared-weights race
     c = make(eval_freq_epochs=1, eval_async=False)
