@@ -49,6 +49,12 @@ class PPOAgent(BaseAgent):
         early_stop = False
         if cfg.target_kl is not None:       # the only per-minibatch host sync, and only when KL early stop is enabled
             early_stop = float(self._metrics_dev[N.M["opt/ppo/approx_kl"]].item()) > float(cfg.target_kl)
+            self.metrics_recorder.record("train", {"opt/ppo/kl_stop_triggered": 1 if early_stop else 0})    # ppo_agent.py:140
         return dict(loss=EngineLoss(self._metrics_dev), early_stop_epoch=early_stop)
 
     losses_for_batch._engine_native = True   # the fused step tail (BaseAgent._fused_training_step) may stand in for it
+
+    def pop_epoch_metrics(self):
+        out = super().pop_epoch_metrics()
+        out.setdefault("opt/ppo/kl_stop_triggered", 0.0)        # without target_kl no minibatch ever triggers (reference: constant 0)
+        return out

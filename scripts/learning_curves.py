@@ -56,7 +56,7 @@ def run_port(seed):
     cfg = c1_config(seed)
     n, T, B = int(cfg.n_envs), int(cfg.n_steps), int(cfg.batch_size)
     torch.manual_seed(seed)
-    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    torch.set_num_threads(int(os.environ.get("GS_PORT_THREADS", "1")))      # 256-sample minibatches: more threads only spin
     env = OE.OracleVecEnv("CartPole-v1", n, seed=seed)
     obs, _ = env.reset()
     params = {k: v.requires_grad_(True) for k, v in P.init_params(4, tuple(cfg.hidden_dims), 2, seed=seed).items()}

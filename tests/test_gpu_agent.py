@@ -168,6 +168,11 @@ def test_target_kl_early_stop_flag():
     agent = build_agent(cfg, rank=0, world_size=1)
     agent.train_one_rollout()   # after the first Adam step approx_kl > 1e-9 -> the remaining passes are skipped
     assert agent._early_stop_epoch is True
+    # reference agents/ppo/ppo_agent.py:140: every evaluated minibatch records the flag; the first (ratio == 1) does not trigger, the second does
+    assert agent.pop_epoch_metrics()["opt/ppo/kl_stop_triggered"] == 0.5
+    free = build_agent(_cfg(n_envs=8, n_steps=32, batch_size=256, model_id="mlp_64x64"), rank=0, world_size=1)
+    free.train_one_rollout()
+    assert free._early_stop_epoch is False and free.pop_epoch_metrics()["opt/ppo/kl_stop_triggered"] == 0.0
 
 
 def test_cartpole_ppo_learns_on_the_reference_configuration():
