@@ -461,6 +461,21 @@ def golden_dataloader():
             errors[tag] = str(e)
     out = dict(data_len=48, batch_size=16, num_passes=3, torch_seed=77, generator_seed=9, length=len(loader), first=first, second=second,
                errors=errors)
+    # `--override KEY=VALUE` handling of the launcher (utils/train_launcher.py:22-53, 81-98): type inference and the two ValueErrors
+    from utils.config import load_config
+    from utils.train_launcher import _apply_config_overrides, _parse_config_overrides
+    items = ["policy_lr=0.001", "n_envs=16", "eval_async=true", "normalize_advantages = rollout", "ent_coef=-0.5", "eval_deterministic=FALSE",
+             "n_steps= 64", "gamma=.9"]
+    cli = dict(items=items, parsed=_parse_config_overrides(items), errors={})
+    cfg = _apply_config_overrides(load_config("CartPole-v1", "ppo"), cli["parsed"])
+    cli["applied"] = {k: getattr(cfg, k) for k in cli["parsed"]}
+    for tag, fn in (("format", lambda: _parse_config_overrides(["policy_lr"])),
+                    ("field", lambda: _apply_config_overrides(load_config("CartPole-v1", "ppo"), {"no_such_field": 1}))):
+        try:
+            fn()
+        except ValueError as e:
+            cli["errors"][tag] = str(e)
+    out["cli_overrides"] = cli
     with open(os.path.join(OUT, "dataloader.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("dataloader:", len(first), "batches per epoch;", errors)

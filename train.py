@@ -32,6 +32,30 @@ def _parse_value(v: str):
         return v
 
 
+def parse_overrides(items) -> dict:
+    """``KEY=VALUE`` strings -> dict (reference utils/train_launcher.py:22-53: bools, ints, floats, else strings; here also
+    ``none`` / scientific notation / JSON lists).  ``ValueError`` for an item without ``=``."""
+    out = {}
+    for item in items or ():
+        if "=" not in item:
+            raise ValueError(f"Invalid override format: {item}. Expected KEY=VALUE")
+        k, v = item.split("=", 1)
+        out[k.strip()] = _parse_value(v.strip())
+    return out
+
+
+def apply_overrides(config, overrides: dict):
+    """reference utils/train_launcher.py:81-98: ``setattr`` after validation, ``ValueError`` for a key that is not a Config field."""
+    from dataclasses import fields
+
+    valid = {f.name for f in fields(config)}
+    for k, v in overrides.items():
+        if k not in valid:
+            raise ValueError(f"Invalid config field: {k}. Not a valid Config attribute.")
+        setattr(config, k, v)
+    return config
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description="Train an agent on the b200 engine.")
     ap.add_argument("config_id", nargs="?", default="CartPole-v1:ppo", help="<env>:<variant>, e.g. CartPole-v1:ppo")
@@ -56,11 +80,7 @@ def main(argv=None) -> int:
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     config = load_config(env_id, variant)
-    for ov in args.override:                      # applied after validation, like the reference (train_launcher.py:81-98)
-        k, _, v = ov.partition("=")
-        if not hasattr(config, k):
-            raise KeyError(f"unknown config key {k!r}")
-        setattr(config, k, _parse_value(v))
+    apply_overrides(config, parse_overrides(args.override))
     if args.max_env_steps is not None:
         config.max_env_steps = args.max_env_steps
     set_random_seed(config.seed)
