@@ -799,39 +799,97 @@ class BaseAgent(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, checkpoint_dir) -> None:
-        """model.pt / optimizer.pt / state.json like the reference (agents/base_agent.py:658-732), plus what the reference cannot
-        resume (TODO.md:29): an exact snapshot of this rank's device envs (physics state, episode accumulators, autoreset flags,
-        reset-stream counters, count-bonus tables), the collector's current observations and running statistics.  Resuming from
-        it continues the run bit for bit.  Rank 0 writes the shared files, every rank its own env shard."""
+        """model.pt / optimizer.pt / state.json in the reference's format (agents/base_agent.py:658-732: state-dict, LIST of optimizer
+        state-dicts, state.json with epoch / total_env_steps / total_vec_steps / run_id / config / best_train_reward / best_val_reward /
+        rng_states), so either side loads the other's checkpoints -- plus what the reference cannot resume (TODO.md:29): an exact
+        snapshot of this rank's device envs (physics state, episode accumulators, autoreset flags, reset-stream counters, count-bonus
+        tables), the collector's current observations and running statistics.  Resuming from it continues the run bit for bit.
+        Rank 0 writes the shared files, every rank its own env shard."""
+        import dataclasses
+        import random
+
         d = Path(checkpoint_dir)
         d.mkdir(parents=True, exist_ok=True)
         col = self.get_rollout_collector("train")
         col._resolve_pending_episodes()
         if self.rank == 0:
+            finite = lambda x: float(x) if math.isfinite(x) else None
             torch.save(self.policy_model.state_dict(), d / "model.pt")
-            torch.save(self.optimizers().state_dict(), d / "optimizer.pt")
-            state = {"epoch": self.current_epoch, "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
-                     "best_episode_reward": col._best_episode_reward if math.isfinite(col._best_episode_reward) else None,
-                     "best_eval_reward": self.best_eval_reward if math.isfinite(self.best_eval_reward) else None,
-                     "algo_id": self.config.algo_id, "env_id": self.config.env_id, "rng_seed": col.rng_seed, "world_size": self.world_size}
-            (d / "state.json").write_text(json.dumps(state, indent=2))
+            torch.save([self.optimizers().state_dict()], d / "optimizer.pt")
+            config = dataclasses.asdict(self.config) if dataclasses.is_dataclass(self.config) else dict(vars(self.config))
+            config["algo_id"] = self.config.algo_id
+            np_state = np.random.get_state()
+            state = {"epoch": int(self.current_epoch), "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
+                     "run_id": getattr(getattr(self, "run", None), "run_id", None), "config": config,
+                     "best_train_reward": finite(col._best_episode_reward),
+                     "best_val_reward": finite(self.get_rollout_collector("val")._best_episode_reward),
+                     "rng_states": {"torch": torch.get_rng_state().tolist(),
+                                    "torch_cuda": [t.tolist() for t in torch.cuda.get_rng_state_all()],
+                                    "numpy": {"state_type": np_state[0], "state_keys": np_state[1].tolist(), "state_pos": int(np_state[2]),
+                                              "state_has_gauss": int(np_state[3]), "state_cached_gaussian": float(np_state[4])},
+                                    "random": random.getstate()},
+                     # engine additions
+                     "best_eval_reward": finite(self.best_eval_reward), "algo_id": self.config.algo_id, "env_id": self.config.env_id,
+                     "rng_seed": col.rng_seed, "world_size": self.world_size}
+            (d / "state.json").write_text(json.dumps(state, indent=2, default=str))
         env = self.get_env("train")
         torch.save({"snapshot": env.snapshot().cpu(), "obs": None if col.obs is None else col.obs.cpu(),
                     "stats": None if col._stats_dev is None else col._stats_dev.cpu(), "n_envs": env.num_envs,
                     "env_id_offset": self.shard.env_id_offset}, d / f"env_state.rank{self.rank}.pt")
 
-    def load_checkpoint(self, checkpoint_dir, *, resume_training: bool = True) -> None:
-        d = Path(checkpoint_dir)
-        self.policy_model.load_state_dict(torch.load(d / "model.pt", map_location=self.device))
-        if not resume_training:
+    def _load_model_state(self, state_dict, strict: bool) -> None:
+        """reference agents/base_agent.py:754-781: strict load, or (transfer learning) only the tensors whose key and shape match."""
+        if strict:
+            self.policy_model.load_state_dict(state_dict, strict=True)
             return
-        self.optimizers().load_state_dict(torch.load(d / "optimizer.pt", map_location=self.device))
+        own = self.policy_model.state_dict()
+        keep = {k: v for k, v in state_dict.items() if k in own and v.shape == own[k].shape}
+        res = self.policy_model.load_state_dict(keep, strict=False)
+        skipped = sum(1 for k, v in state_dict.items() if k in own and v.shape != own[k].shape)
+        if self.rank == 0:
+            print(f"Partial weight loading: {len(keep)} params loaded, {skipped} skipped (size mismatch), {len(res.missing_keys)} missing"
+                  if keep else "Warning: No compatible weights found for transfer learning")
+
+    def load_checkpoint(self, checkpoint_dir, resume_training: bool = True, strict: bool = True, load_optimizer_only: bool = False) -> None:
+        """reference agents/base_agent.py:734-885 (same arguments): weights always; with ``resume_training`` the optimizer state (a list or
+        a single state-dict), then -- unless ``load_optimizer_only`` -- host RNG states, step counters and best rewards; and, when the
+        checkpoint carries this rank's env shard for the same world size, the exact device-env snapshot."""
+        import random
+
+        d = Path(checkpoint_dir)
+        if (d / "model.pt").exists():
+            self._load_model_state(torch.load(d / "model.pt", map_location=self.device, weights_only=True), strict)
+        elif (d / "policy.ckpt").exists():                       # the reference's old single-file format
+            ck = torch.load(d / "policy.ckpt", map_location=self.device, weights_only=False)
+            self._load_model_state(ck.get("model_state_dict", ck), strict)
+        else:
+            raise FileNotFoundError(f"Model checkpoint not found at {d / 'model.pt'} or {d / 'policy.ckpt'}")
+        if not resume_training or not (d / "state.json").exists():
+            return
         state = json.loads((d / "state.json").read_text())
+        if (d / "optimizer.pt").exists():
+            opt_states = torch.load(d / "optimizer.pt", map_location=self.device, weights_only=False)
+            self.optimizers().load_state_dict(opt_states[0] if isinstance(opt_states, (list, tuple)) else opt_states)
+        if load_optimizer_only:
+            return
+        rs = state.get("rng_states")
+        if rs:
+            torch.set_rng_state(torch.tensor(rs["torch"], dtype=torch.uint8))
+            if rs.get("torch_cuda") and len(rs["torch_cuda"]) == torch.cuda.device_count():
+                torch.cuda.set_rng_state_all([torch.tensor(t, dtype=torch.uint8) for t in rs["torch_cuda"]])
+            ns = rs["numpy"]
+            np.random.set_state((ns["state_type"], np.array(ns["state_keys"], dtype=np.uint32), ns["state_pos"], ns["state_has_gauss"],
+                                 ns["state_cached_gaussian"]))
+            random.setstate((rs["random"][0], tuple(rs["random"][1]), rs["random"][2]))
         col = self.get_rollout_collector("train")
-        self.current_epoch = int(state["epoch"])
-        col.total_steps, col.total_vec_steps = int(state["total_env_steps"]), int(state["total_vec_steps"])
-        if state.get("best_episode_reward") is not None:
-            col._best_episode_reward = float(state["best_episode_reward"])
+        self.current_epoch = int(state.get("epoch", 0))
+        col.total_steps = int(state.get("total_env_steps", state.get("total_timesteps", 0)))
+        col.total_vec_steps = int(state.get("total_vec_steps", 0))
+        best_train = state.get("best_train_reward", state.get("best_episode_reward"))
+        if best_train is not None:
+            col._best_episode_reward = float(best_train)
+        if state.get("best_val_reward") is not None:
+            self.get_rollout_collector("val")._best_episode_reward = float(state["best_val_reward"])
         if state.get("best_eval_reward") is not None:
             self.best_eval_reward = float(state["best_eval_reward"])
         shard = d / f"env_state.rank{self.rank}.pt"

@@ -215,6 +215,63 @@ def test_checkpoint_roundtrip(tmp_path):
     assert b.get_rollout_collector("train").total_steps == 256
     assert set(torch.load(tmp_path / "ck" / "model.pt").keys()) == {"backbone.0.weight", "backbone.0.bias", "backbone.2.weight", "backbone.2.bias",
                                                                    "policy_head.weight", "policy_head.bias", "value_head.weight", "value_head.bias"}
+    # the reference's on-disk format (agents/base_agent.py:658-732): optimizer.pt is a LIST of state-dicts, state.json carries its keys
+    import json
+    import random
+
+    opt_states = torch.load(tmp_path / "ck" / "optimizer.pt", weights_only=False)
+    assert isinstance(opt_states, list) and len(opt_states) == 1 and set(opt_states[0]) == {"state", "param_groups"}
+    state = json.loads((tmp_path / "ck" / "state.json").read_text())
+    for k in ("epoch", "total_env_steps", "total_vec_steps", "run_id", "config", "best_train_reward", "best_val_reward", "rng_states"):
+        assert k in state, k
+    assert state["config"]["algo_id"] == "ppo" and state["config"]["n_envs"] == 8 and state["total_vec_steps"] == 32
+    assert set(state["rng_states"]) == {"torch", "torch_cuda", "numpy", "random"}
+    # host RNG streams continue from the checkpoint after a load
+    torch.manual_seed(123); np.random.seed(123); random.seed(123)
+    b.load_checkpoint(tmp_path / "ck")
+    draws = (torch.rand(3).tolist(), np.random.rand(3).tolist(), random.random())
+    b.load_checkpoint(tmp_path / "ck")
+    assert draws == (torch.rand(3).tolist(), np.random.rand(3).tolist(), random.random())
+
+    # a checkpoint WRITTEN THE REFERENCE'S WAY (plain torch state-dicts, its state.json keys only) loads into the engine
+    ref = tmp_path / "ref_ck"
+    ref.mkdir()
+    sd = {k: torch.randn_like(v).cpu() for k, v in a.policy_model.state_dict().items()}
+    torch.save(sd, ref / "model.pt")
+    params = [torch.nn.Parameter(v.clone()) for v in sd.values()]
+    topt = torch.optim.Adam(params, lr=7e-4)
+    for p_ in params:
+        p_.grad = torch.randn_like(p_)
+    topt.step()
+    torch.save([topt.state_dict()], ref / "optimizer.pt")
+    (ref / "state.json").write_text(json.dumps({"epoch": 7, "total_env_steps": 1792, "total_vec_steps": 224, "run_id": "abc123", "best_train_reward": 88.0,
+                                                "best_val_reward": 99.0}))
+    c = build_agent(cfg, rank=0, world_size=1)
+    c.load_checkpoint(ref)
+    for k, v in c.policy_model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    got = c.optimizers().state_dict()
+    assert got["param_groups"][0]["lr"] == 7e-4
+    for i in range(len(params)):
+        assert torch.equal(got["state"][i]["exp_avg"].cpu().reshape(-1), topt.state_dict()["state"][i]["exp_avg"].reshape(-1)), i
+    col = c.get_rollout_collector("train")
+    assert (c.current_epoch, col.total_steps, col.total_vec_steps, col._best_episode_reward) == (7, 1792, 224, 88.0)
+    assert c.get_rollout_collector("val")._best_episode_reward == 99.0
+    c.train_one_rollout()                                    # and training goes on from it
+    # load_optimizer_only: optimizer warm start, fresh counters; strict=False: only tensors whose shape matches; no model file: FileNotFoundError
+    e = build_agent(cfg, rank=0, world_size=1)
+    e.load_checkpoint(ref, load_optimizer_only=True)
+    assert e.current_epoch == 0 and e.get_rollout_collector("train").total_steps == 0 and e.optimizers().state_dict()["param_groups"][0]["lr"] == 7e-4
+    odd = dict(sd)
+    odd["policy_head.weight"] = torch.zeros(5, 64)
+    torch.save(odd, ref / "model.pt")
+    with pytest.raises(RuntimeError):
+        e.load_checkpoint(ref, resume_training=False)
+    before = e.policy_model.policy_head.weight.clone()
+    e.load_checkpoint(ref, resume_training=False, strict=False)
+    assert torch.equal(e.policy_model.policy_head.weight, before) and torch.equal(e.policy_model.value_head.weight.cpu(), sd["value_head.weight"])
+    with pytest.raises(FileNotFoundError):
+        e.load_checkpoint(tmp_path / "nothing_here")
 
 
 @pytest.mark.parametrize("algo,model_id", [("ppo", "mlp_64x64"), ("ppo", "mlp_small"), ("reinforce", "mlp_64x64")])
