@@ -588,50 +588,54 @@ class BaseAgent(nn.Module):
         history = []
         max_epochs = max_epochs if max_epochs is not None else cfg.max_epochs
         reason = ""
-        while True:
-            # on_train_epoch_start: budget check before collecting (reference agents/base_agent.py:306-320)
-            if cfg.max_env_steps is not None:
-                cur = col.total_steps * self.world_size
-                nxt = int(cfg.n_envs) * int(cfg.n_steps)
-                if cur + nxt > cfg.max_env_steps:
-                    reason = f"'train/cnt/total_env_steps': {cur} + {nxt} would exceed {int(cfg.max_env_steps)}."
+        try:
+            while True:
+                # on_train_epoch_start: budget check before collecting (reference agents/base_agent.py:306-320)
+                if cfg.max_env_steps is not None:
+                    cur = col.total_steps * self.world_size
+                    nxt = int(cfg.n_envs) * int(cfg.n_steps)
+                    if cur + nxt > cfg.max_env_steps:
+                        reason = f"'train/cnt/total_env_steps': {cur} + {nxt} would exceed {int(cfg.max_env_steps)}."
+                        break
+                if max_epochs is not None and self.current_epoch >= max_epochs:
+                    reason = f"max_epochs={max_epochs} reached."
                     break
-            if max_epochs is not None and self.current_epoch >= max_epochs:
-                reason = f"max_epochs={max_epochs} reached."
-                break
-            self.train_one_rollout()
-            # on_train_epoch_end: metrics, schedules, early stopping
-            row = {"epoch": self.current_epoch, "time_s": time.time() - t0}
-            row.update({f"train/{k}": v for k, v in col.get_metrics().items() if k != "action_dist"})
-            row.update({f"train/{k}": v for k, v in self.pop_epoch_metrics().items()})
-            row["train/cnt/total_env_steps"] = col.total_steps * self.world_size
-            self._apply_schedules()
-            thr = cfg.early_stop_on_train_threshold
-            if thr and "train/roll/ep_rew/mean" in row:
-                limit = self.get_env("train").get_return_threshold() if thr is True else float(thr)
-                if row["train/roll/ep_rew/mean"] >= limit:
-                    reason = f"train/roll/ep_rew/mean {row['train/roll/ep_rew/mean']:.2f} >= {limit}"
-                    self.should_stop = True
-            if cfg.eval_freq_epochs and (self.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
-                    and self.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
-                self.metrics_recorder.reset_epoch("val")
-                ev = self.validation_epoch()        # synchronous, or the latest finished background evaluation (eval_async)
-                row.update({f"val/{k}": v for k, v in ev.items()})
-                mean = ev.get("roll/ep_rew/mean")
-                if mean is not None:
-                    thr = cfg.early_stop_on_eval_threshold
-                    if thr:
-                        limit = cfg.reward_threshold if cfg.reward_threshold is not None else self.get_env("val").get_return_threshold()
-                        limit = limit if thr is True else float(thr)
-                        if mean >= limit:
-                            reason = f"val/roll/ep_rew/mean {mean:.2f} >= {limit}"
-                            self.should_stop = True
-            history.append(row)
-            if log_fn is not None and self.rank == 0:
-                log_fn(row)
-            self.current_epoch += 1
-            if self.should_stop:
-                break
+                self.train_one_rollout()
+                # on_train_epoch_end: metrics, schedules, early stopping
+                row = {"epoch": self.current_epoch, "time_s": time.time() - t0}
+                row.update({f"train/{k}": v for k, v in col.get_metrics().items() if k != "action_dist"})
+                row.update({f"train/{k}": v for k, v in self.pop_epoch_metrics().items()})
+                row["train/cnt/total_env_steps"] = col.total_steps * self.world_size
+                self._apply_schedules()
+                thr = cfg.early_stop_on_train_threshold
+                if thr and "train/roll/ep_rew/mean" in row:
+                    limit = self.get_env("train").get_return_threshold() if thr is True else float(thr)
+                    if row["train/roll/ep_rew/mean"] >= limit:
+                        reason = f"train/roll/ep_rew/mean {row['train/roll/ep_rew/mean']:.2f} >= {limit}"
+                        self.should_stop = True
+                if cfg.eval_freq_epochs and (self.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
+                        and self.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
+                    self.metrics_recorder.reset_epoch("val")
+                    ev = self.validation_epoch()        # synchronous, or the latest finished background evaluation (eval_async)
+                    row.update({f"val/{k}": v for k, v in ev.items()})
+                    mean = ev.get("roll/ep_rew/mean")
+                    if mean is not None:
+                        thr = cfg.early_stop_on_eval_threshold
+                        if thr:
+                            limit = cfg.reward_threshold if cfg.reward_threshold is not None else self.get_env("val").get_return_threshold()
+                            limit = limit if thr is True else float(thr)
+                            if mean >= limit:
+                                reason = f"val/roll/ep_rew/mean {mean:.2f} >= {limit}"
+                                self.should_stop = True
+                history.append(row)
+                if log_fn is not None and self.rank == 0:
+                    log_fn(row)
+                self.current_epoch += 1
+                if self.should_stop:
+                    break
+        except BaseException as exc:
+            self.on_exception(None, self, exc)
+            raise
         self._early_stop_reason = reason
         self.on_fit_end()
         return {"history": history, "stop_reason": reason, "epochs": self.current_epoch, "elapsed_s": time.time() - t0,
@@ -776,6 +780,14 @@ class BaseAgent(nn.Module):
 
     def on_fit_end(self) -> None:
         self._cleanup_async_eval()
+
+    def on_exception(self, trainer, pl_module, exception) -> None:
+        """reference agents/base_agent.py:509-511: training failed -- stop and join the background evaluation; the training error is the
+        one that propagates, an evaluation error on top of it is dropped."""
+        try:
+            self._cleanup_async_eval()
+        except N.EngineError:
+            pass
 
     def log_dict(self, metrics: Dict[str, Any]) -> None:
         if self.trainer is not None:

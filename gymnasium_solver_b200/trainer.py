@@ -34,6 +34,7 @@ class Callback:
     def on_validation_epoch_start(self, trainer, pl_module) -> None: ...
     def on_validation_epoch_end(self, trainer, pl_module) -> None: ...
     def on_fit_end(self, trainer, pl_module) -> None: ...
+    def on_exception(self, trainer, pl_module, exception) -> None: ...
 
 
 class Trainer:
@@ -45,9 +46,11 @@ class Trainer:
         self.current_epoch = 0
         self.logged_metrics: Dict[str, Any] = {}
 
-    def _call(self, hook: str, agent) -> None:
+    def _call(self, hook: str, agent, *args) -> None:
         for cb in self.callbacks:
-            getattr(cb, hook)(self, agent)
+            fn = getattr(cb, hook, None)          # callbacks written against Lightning need not define every hook
+            if fn is not None:
+                fn(self, agent, *args)
 
     def log_dict(self, metrics: Dict[str, Any]) -> None:
         self.logged_metrics.update(metrics)
@@ -60,24 +63,30 @@ class Trainer:
         agent.on_fit_start()
         self._call("on_fit_start", agent)
         max_epochs = self.max_epochs if self.max_epochs is not None else cfg.max_epochs
-        while not self.should_stop:
-            if max_epochs is not None and agent.current_epoch >= max_epochs:
-                agent.set_early_stop_reason(f"max_epochs={max_epochs} reached.")
-                break
-            self.current_epoch = agent.current_epoch
-            self._call("on_train_epoch_start", agent)
-            if not agent.on_train_epoch_start():            # env-step budget exhausted: no rollout is collected (base_agent.py:306-320)
-                self.should_stop = True
-                break
-            agent.train_on_rollout(agent._trajectories)
-            agent.get_rollout_collector("train").resolve_episodes_async()
-            self._call("on_train_epoch_end", agent)
-            if cfg.eval_freq_epochs and (agent.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
-                    and agent.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
-                self._call("on_validation_epoch_start", agent)
-                agent.validation_epoch()
-                self._call("on_validation_epoch_end", agent)
-            agent.current_epoch += 1
+        try:
+            while not self.should_stop:
+                if max_epochs is not None and agent.current_epoch >= max_epochs:
+                    agent.set_early_stop_reason(f"max_epochs={max_epochs} reached.")
+                    break
+                self.current_epoch = agent.current_epoch
+                self._call("on_train_epoch_start", agent)
+                if not agent.on_train_epoch_start():            # env-step budget exhausted: no rollout is collected (base_agent.py:306-320)
+                    self.should_stop = True
+                    break
+                agent.train_on_rollout(agent._trajectories)
+                agent.get_rollout_collector("train").resolve_episodes_async()
+                self._call("on_train_epoch_end", agent)
+                if cfg.eval_freq_epochs and (agent.current_epoch + 1) % int(cfg.eval_freq_epochs) == 0 \
+                        and agent.current_epoch + 1 >= int(cfg.eval_warmup_epochs):
+                    self._call("on_validation_epoch_start", agent)
+                    agent.validation_epoch()
+                    self._call("on_validation_epoch_end", agent)
+                agent.current_epoch += 1
+        except BaseException as exc:                        # Lightning's on_exception: callbacks, then the module (joins a background evaluation)
+            self._call("on_exception", agent, exc)
+            if hasattr(agent, "on_exception"):
+                agent.on_exception(self, agent, exc)
+            raise
         if hasattr(agent, "on_fit_end"):                     # module hook (Lightning calls it when defined): joins a background evaluation
             agent.on_fit_end()
         self._call("on_fit_end", agent)

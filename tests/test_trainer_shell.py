@@ -137,3 +137,34 @@ def test_trainer_drives_hooks_in_the_reference_order(tmp_path):
         def on_train_epoch_end(self, t, m): t.should_stop = True
     col.total_steps, agent.current_epoch = 0, 0
     assert Trainer(callbacks=[Stop()], max_epochs=10).fit(agent)["epochs"] == 1
+
+
+def test_trainer_reports_a_training_failure_through_on_exception():
+    """Lightning's on_exception protocol (reference agents/base_agent.py:509-511 joins its background evaluation there): callbacks first,
+    then the module, then the error propagates; on_fit_end hooks do not run; a callback without the hook is skipped."""
+    log = []
+
+    class Spy(Callback):
+        def on_exception(self, t, m, exc): log.append(f"cb.exception({exc})")
+        def on_fit_end(self, t, m): log.append("cb.fit_end")
+
+    class Bare:                                             # a Lightning-style callback that defines only what it needs
+        def on_train_epoch_start(self, t, m): log.append("bare.epoch_start")
+
+    col = SimpleNamespace(total_steps=0, resolve_episodes_async=lambda: None)
+    agent = SimpleNamespace(config=SimpleNamespace(max_epochs=None, eval_freq_epochs=None, eval_warmup_epochs=0), current_epoch=0, world_size=1,
+                            best_eval_reward=float("-inf"), _early_stop_reason="", _fit_t0=0.0, _trajectories=None, trainer=None)
+    agent.on_fit_start = lambda: None
+    agent.get_rollout_collector = lambda stage: col
+    agent.on_train_epoch_start = lambda: True
+    agent.on_fit_end = lambda: log.append("agent.fit_end")
+    agent.on_exception = lambda t, m, exc: log.append(f"agent.exception({exc})")
+
+    def train(traj):
+        if agent.current_epoch == 2:
+            raise RuntimeError("kernel failed")
+
+    agent.train_on_rollout = train
+    with pytest.raises(RuntimeError, match="kernel failed"):
+        Trainer(callbacks=[Spy(), Bare()]).fit(agent)
+    assert log == ["bare.epoch_start"] * 3 + ["cb.exception(kernel failed)", "agent.exception(kernel failed)"]
