@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Learning curves of BASELINE.json's C1 configuration (CartPole-v1:ppo as shipped: 8 envs x 32 steps, 256x256 MLP, 20 passes of one
+"""(dev tool; lives under tests/ because its ``--arm port`` leg runs the oracle, which only tests / smoke / the bench baseline may do)
+
+Learning curves of BASELINE.json's C1 configuration (CartPole-v1:ppo as shipped: 8 envs x 32 steps, 256x256 MLP, 20 passes of one
 256-sample minibatch, gamma .98, lambda .8, clip .1, Adam 1e-3, 1e5 env steps) on the two arms:
 
   --arm engine   the CUDA engine (needs a GPU): build_agent(load_config("CartPole-v1", "ppo")).learn() without early stopping

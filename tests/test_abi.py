@@ -52,6 +52,11 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f"{f} references the oracle"
+    # the launcher and the measurement scripts are product-side too: only tests/, smoke() and bench.py's CPU-baseline leg may run the oracle
+    extra = [os.path.join(ROOT, "train.py")] + [os.path.join(ROOT, "scripts", f) for f in os.listdir(os.path.join(ROOT, "scripts")) if f.endswith(".py")]
+    for path in extra:
+        text = open(path).read()
+        assert "import oracle" not in text and "from oracle" not in text, f"{path} references the oracle"
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
