@@ -108,11 +108,14 @@ def ppo_grads(p, obs, actions, old_logp, values_old, adv, ret, fmt, clip=0.2, cl
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=262144)
+    ap.add_argument("--hidden", type=int, default=64, help="width of both hidden layers (64: the bench network; 128 / 256: the C4 presets)")
+    ap.add_argument("--obs-dim", type=int, default=4)
+    ap.add_argument("--actions", type=int, default=2)
     args = ap.parse_args()
-    n, D, A = args.n, 4, 2
+    n, D, A, Hd = args.n, args.obs_dim, args.actions, args.hidden
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(7)
-    p = P.random_params(D, (64, 64), A, seed=3, has_value=True)
+    p = P.random_params(D, (Hd, Hd), A, seed=3, has_value=True)
     obs = torch.randn(n, D, generator=g)
     actions = torch.randint(0, A, (n,), generator=g)
     with torch.no_grad():
@@ -127,7 +130,7 @@ def main():
     _, ref, _ = P.loss_and_grads(P.ppo_loss, p64, obs.double(), actions, old_logp.double(), values_old.double(), adv.double(), ret.double(), **hp)
     ref = ref.numpy()
     scale = np.abs(ref).max()
-    print(f"PPO gradients of the 64x64 network, {n:,}-sample minibatch, against an fp64 autograd reference (gradient scale max|g| = {scale:.3e};"
+    print(f"PPO gradients of the {Hd}x{Hd} network (obs {D}, actions {A}), {n:,}-sample minibatch, against an fp64 autograd reference (gradient scale max|g| = {scale:.3e};"
           f" north_star tolerance: 1e-4 of it)\n")
     print("| operand format of the four tensor-core GEMM groups | MMAs per product (K per instruction) | max abs error / scale | relative L2 error |")
     print("|---|---|---|---|")
