@@ -12,6 +12,10 @@ What runs unmodified from /root/reference:
   gym_wrappers/MountainCarV0/state_count_bonus.py, gym_wrappers/MountainCarV0/reward_shaper.py,
   gym_wrappers/CartPoleV1/reward_shaper.py (the per-env reward wrappers, stepped over a scripted sub-env that replays a
   physics trajectory; see golden_wrappers)
+  utils/dataloaders.py (build_index_collate_loader_from_collector over a recording collector) and utils/train_launcher.py
+  (_parse_config_overrides / _apply_config_overrides)  -> dataloader.json
+  trainer_callbacks/hyperparameter_scheduler.py, utils/schedule_resolver.py, utils/rollout_stats.py, utils/config.py::load_config,
+  utils/torch.py helpers, utils/samplers.py  -> host_logic.json;  utils/models.py construction + init  -> model_init.npz
 Shims: the reference's own Lightning stub (tests/conftest.py:15-81) and a stub `gymnasium` module (the real
 package is absent here); neither touches the arithmetic above.  REINFORCE needs config.normalize_advantages
 supplied because the reference reads a field REINFORCEConfig lacks.
