@@ -9,8 +9,8 @@ split exactly as the hardware would see them, products and sums in fp32 like the
 fp64 autograd reference (oracle/policy.py) on the same minibatch:
 
   fp32        operands untouched (what the fp32 FMA-pipe kernel computes)
-  tf32x3      hi = top 19 bits (the tensor core TRUNCATES tf32 operands), lo = trunc19(x - hi);  hi*hi + lo*hi + hi*lo      3 MMAs, K=8
-  tf32x1      hi*hi                                                                                                           1 MMA,  K=8
+  tf32x3      hi = rn_tf32(x) (tc_common.cuh::tf32_rn), lo = x - hi, read by the tensor core as its top 19 bits;  hi*hi + lo*hi + hi*lo   3 MMAs, K=8
+  tf32x1      the fp32 operand as the tensor core reads it (top 19 bits: TRUNCATED)                                          1 MMA,  K=8
   bf16x3      b0 = rn_bf16(x), b1 = rn_bf16(x - b0);  b0*b0 + b1*b0 + b0*b1                                                   3 MMAs, K=16
   bf16x6      b0, b1, b2 = three bf16 terms;  all products down to 2^-24: b0b0 + b0b1 + b1b0 + b1b1 + b0b2 + b2b0            6 MMAs, K=16
   bf16x1      b0*b0                                                                                                           1 MMA,  K=16
@@ -36,10 +36,17 @@ def bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def rn_tf32(x: torch.Tensor) -> torch.Tensor:
+    """tc_common.cuh::tf32_rn: round-half-away on the 13 dropped mantissa bits."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def split(x, fmt):
+    if fmt == "tf32x1":
+        return [trunc19(x)]                        # a bare fp32 operand: the tensor core reads its top 19 bits
     if fmt.startswith("tf32"):
-        hi = trunc19(x)
-        return [hi, trunc19(x - hi)]
+        hi = rn_tf32(x)                            # what update_tc.cu stores: hi rounded to nearest, lo = x - hi exact in fp32 ...
+        return [hi, trunc19(x - hi)]               # ... of which the tensor core reads the top 19 bits
     b0 = bf16(x)
     b1 = bf16(x - b0)
     return [b0, b1, bf16(x - b0 - b1)]
