@@ -402,9 +402,12 @@ class BaseAgent(nn.Module):
                     yield p, k, self._make_batch(tm, traj.T, traj.n_envs, n=B, perm_key=key, perm_offset=k * B, perm_len=total, idx_map=idx_map)
 
     def _pack_rollout(self, traj: DeviceTrajectory) -> None:
-        """One 64-byte record per sample (gs_rollout_pack) so the tensor-core update kernel gathers a minibatch sample with a
-        single aligned access.  Only the 64x64 network has that kernel; the buffer is reused across rollouts."""
-        if tuple(getattr(self.config, "hidden_dims", ())) != (64, 64) or "packed" in traj.tm:
+        """One 64-byte record per sample (gs_rollout_pack: the bf16x3 layer-1 operand row + the sample's scalars) so the tensor-core
+        update kernel copies a minibatch sample straight into its operand tile with one aligned access.  The 64x64 and 128x128
+        networks have that kernel (observations of up to 7 features); the buffer is reused across rollouts."""
+        if tuple(getattr(self.config, "hidden_dims", ())) not in ((64, 64), (128, 128)) or "packed" in traj.tm:
+            return
+        if traj.tm["obs"].shape[-1] > 7:
             return
         total = traj.T * traj.n_envs
         buf = getattr(self, "_packed_records", None)

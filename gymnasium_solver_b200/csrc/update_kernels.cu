@@ -425,11 +425,11 @@ __device__ __forceinline__ void finalize_metrics_body(const double* __restrict__
 // One launch folds the per-CTA partials: blocks 0 .. n_red-1 sum the partial gradient vectors in CTA order (deterministic),
 // the last block turns the metric partials into the metric vector.
 __global__ void reduce_and_finalize_kernel(const float* __restrict__ partials, int n_cta, int64_t P, int64_t pstride, float* __restrict__ grads,
-                                           const double* __restrict__ metric_partials, int algo, int H1, int H2, int track, float vf_coef,
+                                           const double* __restrict__ metric_partials, int n_metric_cta, int algo, int H1, int H2, int track, float vf_coef,
                                            float ent_coef, int normalize_adv, int normalize_ret, const uint32_t* __restrict__ dead,
                                            double* __restrict__ metrics) {
     if (blockIdx.x == gridDim.x - 1) {
-        finalize_metrics_body(metric_partials, n_cta, algo, H1, H2, track, vf_coef, ent_coef, normalize_adv, normalize_ret, dead, metrics);
+        finalize_metrics_body(metric_partials, n_metric_cta, algo, H1, H2, track, vf_coef, ent_coef, normalize_adv, normalize_ret, dead, metrics);
         return;
     }
     if (!partials) return;                      // atomic-accumulation configurations have no partial vectors
@@ -643,22 +643,6 @@ __global__ void clip_scale_kernel(float* __restrict__ g, int64_t P, const double
     }
 }
 
-// ---- packed sample records: one 64-byte row per (t,n) so the minibatch gather is a single aligned access per sample ----------
-__global__ void rollout_pack_kernel(BatchDev b, float* __restrict__ packed) {
-    const int64_t total = (int64_t)b.T * b.N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float x[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) x[d] = d < b.D ? __ldcs(b.obs + i * b.D + d) : 0.f;
-        float4* dst = reinterpret_cast<float4*>(packed + i * GS_RECORD_FLOATS);
-        __stcs(dst + 0, make_float4(x[0], x[1], x[2], x[3]));
-        __stcs(dst + 1, make_float4(x[4], x[5], x[6], x[7]));
-        __stcs(dst + 2, make_float4(__int_as_float(__ldcs(b.actions + i)), __ldcs(b.logp_old + i), b.values_old ? __ldcs(b.values_old + i) : 0.f,
-                                    __ldcs(b.adv + i)));
-        __stcs(dst + 3, make_float4(__ldcs(b.ret + i), 0.f, 0.f, 0.f));
-    }
-}
-
 // grad norms + clip of a small parameter vector in ONE block: group sums of squares in a fixed order, then the scaling pass
 __global__ void __launch_bounds__(1024) clip_grad_norm_kernel(float* __restrict__ g, ParamOffsets po, float max_norm, double* __restrict__ metrics) {
     __shared__ double scratch[32];
@@ -765,11 +749,20 @@ static UpdateWs carve(void* ws, const gs_mlp_t* m, int grid) {
     return w;
 }
 
-// tensor-core kernel of update_tc.cu (64x64 networks)
+// tensor-core kernels of update_f16.cu (H x H networks, H = 64 / 128, obs_dim <= 7)
 template <int ALGO>
-int launch_update_tc(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
-                     const uint32_t* offs, float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead, int grid,
-                     cudaStream_t st);
+int launch_update_f16(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
+                     const uint32_t* offs, const void* records, float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead,
+                     int grid, cudaStream_t st);
+int f16_sets(int H);
+int launch_rollout_pack(const BatchDev& b, void* packed, int device, cudaStream_t st);
+int launch_batch_pack(const BatchDev& b, const uint32_t* offs, void* packed, cudaStream_t st);
+
+// does the tensor-core kernel serve this network / rollout?  (everything else runs update_kernel on the fp32 FMA pipe)
+static int update_impl();
+static bool tensor_path_for(int h1, int h2, int obs_dim, int64_t T, int64_t N) {
+    return h1 == h2 && (h1 == 64 || h1 == 128) && obs_dim <= 7 && update_impl() == 0 && T * N < (1ll << 32);
+}
 
 // Sample-id translation of the whole minibatch in one pass: offs[pos] = time-major offset of minibatch position pos.  The
 // keyed Feistel walk + env-major -> time-major division is a ~1000-instruction dependent chain per sample (cycle walking
@@ -796,7 +789,7 @@ __global__ void gather_offsets_kernel(BatchDev b, uint32_t* __restrict__ offs, c
     }
 }
 
-// 0 = tensor cores where a kernel exists (64x64), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
+// 0 = tensor cores where a kernel exists (64x64, 128x128), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
 static int g_update_impl = -1;
 static int update_impl() {
     if (g_update_impl < 0) {
@@ -817,8 +810,7 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     const size_t smem = (size_t)C::kSmemFloats * sizeof(float);
     const int64_t pstride = (P + 3) & ~3ll;   // 16-byte aligned partial vectors
     const MlpDev md = to_dev(m);
-    if (!C::kPersist) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
-    int n_partials = grid;
+    int n_partials = grid, n_metric_partials = grid;
     // batch-normalisation moments the caller did not supply are taken over this minibatch, in the gather pass where there is one
     const float* mf0 = (hp.normalize_adv && !adv_mom) ? b.adv : nullptr;
     const float* mf1 = (hp.normalize_ret && !ret_mom) ? b.ret : nullptr;
@@ -827,7 +819,8 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     if (track || mf0 || mf1 || b.defer_reduce) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead) + 64, st));
     if (mf0) adv_mom = w.sq;
     if (mf1) ret_mom = w.sq + 3;
-    const bool tensor_path = C::H1 == 64 && C::H2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
+    const bool tensor_path = tensor_path_for(C::H1, C::H2, md.D, b.T, b.N);
+    if (!C::kPersist && !tensor_path) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
     if (!tensor_path && (mf0 || mf1)) {
         int64_t blocks = (b.n + 255) / 256;
         const int cap = 4 * sm_count(device);
@@ -843,8 +836,21 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
         }
         const int64_t tiles128 = (b.n + 127) / 128;
         const int sms = sm_count(device);
-        n_partials = (int)(tiles128 < sms ? tiles128 : sms);
-        if (launch_update_tc<ALGO>(md, b, hp, track, adv_mom, ret_mom, offs, w.grad_partials, pstride, w.metric_partials, w.dead, n_partials, st)) return -1;
+        const int ctas = (int)(tiles128 < sms ? tiles128 : sms);
+        n_partials = ctas * f16_sets(C::H1);
+        n_metric_partials = ctas;
+        const void* records = b.packed;
+        const uint32_t* koffs = offs;
+        void* scratch = nullptr;
+        if (!records) {     // no rollout records (gs_rollout_pack): build this minibatch's records in minibatch order (stream-ordered scratch)
+            GS_CUDA(cudaMallocAsync(&scratch, (size_t)b.n * GS_RECORD_FLOATS * 4, st));
+            if (launch_batch_pack(b, offs, scratch, st)) return -1;
+            records = scratch;
+            koffs = nullptr;
+        }
+        const int rc = launch_update_f16<ALGO>(md, b, hp, track, adv_mom, ret_mom, koffs, records, w.grad_partials, pstride, w.metric_partials, w.dead, ctas, st);
+        if (scratch) GS_CUDA(cudaFreeAsync(scratch, st));
+        if (rc) return -1;
     } else {
         auto kern = track ? update_kernel<C, ALGO, true> : update_kernel<C, ALGO, false>;
         GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -852,9 +858,9 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
         GS_LAUNCH_CHECK();
     }
     if (b.defer_reduce) return 0;             // gs_update_finish folds the partials (same n_partials: partials_for())
-    const int grid_used = n_partials;
-    reduce_and_finalize_kernel<<<(unsigned)((P + 255) / 256) + 1, 256, 0, st>>>(C::kPersist ? w.grad_partials : nullptr, grid_used, P, pstride,
-                                                                                  grads_flat, w.metric_partials, ALGO, m->hidden1, m->hidden2,
+    const bool have_partials = C::kPersist || tensor_path;
+    reduce_and_finalize_kernel<<<(unsigned)((P + 255) / 256) + 1, 256, 0, st>>>(have_partials ? w.grad_partials : nullptr, n_partials, P, pstride, grads_flat,
+                                                                                  w.metric_partials, n_metric_partials, ALGO, m->hidden1, m->hidden2,
                                                                                   track ? 1 : 0, hp.vf_coef, hp.ent_coef, hp.normalize_adv,
                                                                                   hp.normalize_ret, w.dead, metrics);
     GS_LAUNCH_CHECK();
@@ -935,17 +941,11 @@ int gs_batch_moments(const gs_batch_t* batch, const float* field, double* out, v
 int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream) {
     if (!batch || !packed) GS_FAIL("gs_rollout_pack: NULL argument");
     if (!batch->obs || !batch->actions || !batch->logp_old || !batch->adv || !batch->ret) GS_FAIL("gs_rollout_pack: batch has NULL arrays");
-    if (batch->T <= 0 || batch->N <= 0 || batch->obs_dim <= 0 || batch->obs_dim > 8) GS_FAIL("gs_rollout_pack: bad shape");
+    if (batch->T <= 0 || batch->N <= 0 || batch->obs_dim <= 0 || batch->obs_dim > 7) GS_FAIL("gs_rollout_pack: bad shape (obs_dim 1..7)");
     if (((uintptr_t)packed & 15) != 0) GS_FAIL("gs_rollout_pack: packed must be 16-byte aligned");
     int device = 0;
     GS_CUDA(cudaGetDevice(&device));
-    const int64_t total = (int64_t)batch->T * batch->N;
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = 16ll * sm_count(device);
-    if (blocks > cap) blocks = cap;
-    rollout_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(to_dev(batch), packed);
-    GS_LAUNCH_CHECK();
-    return 0;
+    return launch_rollout_pack(to_dev(batch), packed, device, (cudaStream_t)stream);
 }
 
 int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv, int want_ret, double* moments, void* workspace,
@@ -962,7 +962,7 @@ int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv,
     GS_CUDA(cudaMemsetAsync(moments, 0, 6 * sizeof(double), st));
     const float* f0 = want_adv ? b.adv : nullptr;
     const float* f1 = want_ret ? b.ret : nullptr;
-    const bool tensor_path = mlp->hidden1 == 64 && mlp->hidden2 == 64 && update_impl() == 0 && (int64_t)b.T * b.N < (1ll << 32);
+    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->obs_dim, b.T, b.N);
     if (tensor_path) {
         const UpdateWs w = carve(workspace, mlp, update_grid(device));
         gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, b.offsets ? b.offsets : w.offs, f0, f1, moments);
@@ -1103,13 +1103,19 @@ int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_fini
     // the partial vectors the deferred step left behind (mirrors launch_update_cfg)
     const bool persist = mlp->hidden1 <= 64 && mlp->hidden2 <= 64;
     const int S = (mlp->hidden1 <= 64) ? 128 : 64;
-    const int64_t n_tiles = (batch->n + S - 1) / S;
+    int64_t n_tiles = (batch->n + S - 1) / S;
     const int grid_max = update_grid(device);
     int n_cta = (int)(n_tiles < grid_max ? n_tiles : grid_max);
-    const bool tensor_path = mlp->hidden1 == 64 && mlp->hidden2 == 64 && update_impl() == 0 && (int64_t)batch->T * batch->N < (1ll << 32);
-    if (tensor_path) { const int sms = sm_count(device); n_cta = (int)(n_tiles < sms ? n_tiles : sms); }
-    f.partials = persist ? w.grad_partials : nullptr;
-    f.n_cta = n_cta; f.n_metric_cta = n_cta;
+    int n_metric_cta = n_cta;
+    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->obs_dim, batch->T, batch->N);
+    if (tensor_path) {
+        const int sms = sm_count(device);
+        n_tiles = (batch->n + 127) / 128;
+        n_metric_cta = (int)(n_tiles < sms ? n_tiles : sms);
+        n_cta = n_metric_cta * f16_sets(mlp->hidden1);
+    }
+    f.partials = (persist || tensor_path) ? w.grad_partials : nullptr;
+    f.n_cta = n_cta; f.n_metric_cta = n_metric_cta;
     f.P = P; f.pstride = (P + 3) & ~3ll;
     f.metric_partials = w.metric_partials;
     f.algo = fin->algo; f.H1 = mlp->hidden1; f.H2 = mlp->hidden2; f.track = fin->track_activations ? 1 : 0;

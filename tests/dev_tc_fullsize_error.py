@@ -30,6 +30,10 @@ loss, flat, om = P.loss_and_grads(P.ppo_loss, {k: v_.double() for k, v_ in p.ite
                                   sel(values_old).double(), sel(adv).double(), sel(ret).double(), clip_range=0.2, clip_range_vf=0.2,
                                   vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
 ref = flat.numpy()
+loss32, flat32, _ = P.loss_and_grads(P.ppo_loss, p, sel(obs), sel(actions), sel(old_logp), sel(values_old), sel(adv), sel(ret), clip_range=0.2,
+                                     clip_range_vf=0.2, vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
+ref32 = flat32.numpy()
+print(f"torch fp32 oracle vs fp64: L2 rel {np.linalg.norm(ref32-ref)/np.linalg.norm(ref):.3e}  |ref| {np.linalg.norm(ref):.3e}")
 names = []
 for k in P.PARAM_ORDER:
     names += [k] * p[k].numel()
@@ -38,7 +42,7 @@ for impl in (0, 1):
     N.lib().gs_set_update_impl(impl)
     g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, hp)
     err = np.abs(g_raw - ref)
-    print(f"impl {impl}: max|ref| {np.abs(ref).max():.3e}  L2 rel {np.linalg.norm(g_raw-ref)/np.linalg.norm(ref):.3e}")
+    print(f"impl {impl}: max|ref| {np.abs(ref).max():.3e}  L2 rel vs fp64 {np.linalg.norm(g_raw-ref)/np.linalg.norm(ref):.3e}  vs torch fp32 {np.linalg.norm(g_raw-ref32)/np.linalg.norm(ref32):.3e}  max abs err / max|ref| {np.abs(g_raw-ref).max()/np.abs(ref).max():.3e}")
     for k in P.PARAM_ORDER:
         sel_ = names == k
         print(f"   {k}: max abs err {err[sel_].max():.3e}  max|ref| {np.abs(ref[sel_]).max():.3e}  mean signed rel {np.mean((g_raw[sel_]-ref[sel_])/ (np.abs(ref[sel_])+1e-12)):.2e}")

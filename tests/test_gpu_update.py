@@ -401,8 +401,9 @@ def test_step_takes_minibatch_moments_itself_when_none_are_given(algo, impl):
 
 @pytest.mark.parametrize("D,A", [(4, 2), (6, 3), (2, 3)])
 def test_packed_sample_records_layout_and_identical_update(D, A):
-    """gs_rollout_pack writes {obs (zero padded to 8), action bits, logp_old, values_old, adv, ret, 0, 0, 0} per (t, n); the update
-    step that gathers from the records returns bit-identical gradients and metrics to the one that gathers the seven arrays."""
+    """gs_rollout_pack writes one 64-byte record per (t, n): the fp16x3 layer-1 operand row x16 = [x_hi (cols 0..D-1), x_lo (cols 7..7+D-1),
+    1, 1 (cols 14, 15)] in fp16 followed by {action bits, logp_old, values_old, adv, ret, 0, 0, 0}; the update step that gathers rollout records
+    returns bit-identical gradients and metrics to the one that builds the minibatch's records from the seven arrays."""
     import engine_api as E
     from gymnasium_solver_b200 import _native as N
 
@@ -419,8 +420,14 @@ def test_packed_sample_records_layout_and_identical_update(D, A):
         batch, keep = E.make_batch(T, Nn, *[E.cu(a) for a in arrs], n=4096, perm_key=5, perm_offset=1000, perm_len=total)
         if use_packed:
             rec = E.pack_rollout(batch, keep).cpu().numpy()
-            np.testing.assert_array_equal(rec[:, :D], obs.reshape(total, D).numpy())
-            assert (rec[:, D:8] == 0).all() and (rec[:, 13:] == 0).all()
+            x = obs.reshape(total, D)
+            x_hi = x.to(torch.float16)
+            x_lo = (x - x_hi.float()).to(torch.float16)
+            half = rec[:, :8].copy().view(np.uint16).reshape(total, 16)
+            np.testing.assert_array_equal(half[:, :D], x_hi.view(torch.int16).numpy().view(np.uint16))
+            np.testing.assert_array_equal(half[:, 7:7 + D], x_lo.view(torch.int16).numpy().view(np.uint16))
+            assert (half[:, D:7] == 0).all() and (half[:, 7 + D:14] == 0).all() and (half[:, 14:] == 0x3C00).all()
+            assert (rec[:, 13:] == 0).all()
             np.testing.assert_array_equal(rec[:, 8].view(np.int32), actions.reshape(total).numpy().astype(np.int32))
             for col, a in zip((9, 10, 11, 12), arrs[2:]):
                 np.testing.assert_array_equal(rec[:, col], a.reshape(total).numpy().astype(np.float32))
