@@ -111,7 +111,7 @@ def build_agent_for_bench(args, rank, world):
 def launches_per_step(cfg, world):
     """Engine kernels launched per training iteration (ours; torch's optimizer / bookkeeping kernels are not counted)."""
     n_mb = (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs)
-    tensor_path = tuple(cfg.hidden_dims) == (64, 64)
+    tensor_path = tuple(cfg.hidden_dims) in ((64, 64), (128, 128))
     per_rollout = 1 + 2 + 1 + 2 + (1 if tensor_path else 0)   # collect, obs/reward moments, gae, adv/ret moments, rollout_pack
     # tensor path: gather pass (offsets + batch moments; all of a rollout's up front when sharded), update kernel,
     # gs_update_finish (reduction + NVLink gradient mean + metrics + clip + Adam).  FMA-pipe path: batch moments, update, finish.
@@ -254,11 +254,11 @@ def kernel_rooflines(agent, cfg, dev):
         return a.elapsed_time(b) / reps * 1e-3
 
     # the update kernel ALONE: every minibatch is prepared first (gather pass: sample offsets + minibatch moments into its own
-    # buffers), so a timed call launches only update_tc_kernel (deferred reduction); a different minibatch every call
+    # buffers), so a timed call launches only update_f16_kernel (deferred reduction); a different minibatch every call
     agent._pack_rollout(traj)          # as train_on_rollout does: 64-byte sample records for the tensor-core kernel's gather
     batches = [b for _, _, b in agent.minibatches(traj, 12345)][:8]
     hd = tuple(cfg.hidden_dims)
-    tensor_path = hd == (64, 64) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
+    tensor_path = hd in ((64, 64), (128, 128)) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
     if tensor_path:
         offs = torch.empty(len(batches), agent.local_batch_size, dtype=torch.int32, device=dev)
         mom = torch.zeros(len(batches), 6, dtype=torch.float64, device=dev)
@@ -279,23 +279,24 @@ def kernel_rooflines(agent, cfg, dev):
     traffic_table = json.load(open(tp)) if os.path.exists(tp) else {}
     full_size = (int(cfg.n_steps), agent.local_n_envs, agent.local_batch_size) == (128, 65536, 1048576)   # the captures' launch sizes
     tr = lambda name: traffic_table.get(name, {}).get("dram_bytes_per_launch") if full_size else None
-    traffic = tr("update_tc_kernel" if tensor_path else "update_kernel")
+    traffic = tr("update_f16_kernel" if tensor_path else "update_kernel")
     if tensor_path:
-        # 144 tcgen05.mma (K=8 tf32) per 128-sample tile; two issuing warps sustain one MMA per ~33 cycles (probes/tc_rate.cu)
+        # tensor-pipe floor of a 128-sample tile from the measured per-instruction costs (probes/bf16_rate.cu, cycles per tcgen05.mma K=16:
+        # M=128 N=16: 40, N=64: 50, N=128: 66; M=64 N=16: 25, N=64: 34, N=80: 42): 64x64: 93 MMAs = 3,464 cycles; 128x128: 141 MMAs
         tiles_per_sm = -(-(agent.local_batch_size // 128) // 148)
-        mma_floor_s = tiles_per_sm * 144 * 33.0 / (peaks["sm_max_mhz"] * 1e6)
-        out["update"] = {"kernel": "update_tc_kernel<PPO> (gs_ppo_step: tcgen05 kind::tf32, 3xTF32 split, TMEM accumulators)", "bound": "tensor",
+        tile_cycles = 3464.0 if hd == (64, 64) else (3 * 66 + 24 * 66 + 16 * 40 + 66 + 16 * 40 + 24 * 66 + 16 * 72 + 8 * 66 + 16 * 40)
+        mma_floor_s = tiles_per_sm * tile_cycles / (peaks["sm_max_mhz"] * 1e6)
+        out["update"] = {"kernel": f"update_f16_kernel<{hd[0]}, PPO> (gs_ppo_step: tcgen05 kind::f16, fp16x3 split, TMEM accumulators)", "bound": "tensor",
                          "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"],
                          "traffic": traffic,
-                         "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the 64x64 MLP, 27,264 per sample) / average launch time of "
-                                 "update_tc_kernel alone (CUDA events on the launching stream, 20 launches on 8 different prepared minibatches); "
-                                 "peak = measured dense bf16 (burst: the kernel is timed alone); traffic = ncu dram bytes of one launch "
-                                 "(profiles/r1d_update_tc_and_finish_ncu_details.md; algorithmic 71 MB). "
-                                 "fp32 parity (1e-4) costs 3 tf32 MMAs per product, and K=8 tf32 MMAs with N<=72 are bound by a per-instruction "
-                                 f"floor, not by math: tensor-pipe floor of this launch {mma_floor_s * 1e3:.3f} ms; the rest is SIMT work between the "
-                                 f"MMAs (profiles/r1d_*). Same arithmetic on the FMA pipe (GS_UPDATE_IMPL=simt): 1.09 ms; fp32 FMA peak {fp32_peak:.1f} TF/s",
+                         "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the MLP, 27,264 per sample for 64x64) / average launch time of "
+                                 "update_f16_kernel alone (CUDA events on the launching stream, 20 launches on 8 different prepared minibatches); "
+                                 "peak = measured dense bf16 (burst: the kernel is timed alone); traffic = ncu dram bytes of one launch (profiles/traffic.json; "
+                                 "algorithmic 71 MB). fp32 parity (1e-4) costs 3 fp16 MMAs per product (x3 the algorithmic flops on the pipe), and the K=16 MMAs of a "
+                                 "64-wide network (N <= 80) are bound by a ~25-50 cycle per-instruction floor, not by math: tensor-pipe floor of this launch "
+                                 f"{mma_floor_s * 1e3:.3f} ms (tiles per SM x measured cycles per tile); fp32 FMA peak {fp32_peak:.1f} TF/s",
                          "algorithmic_flop_per_launch": flops, "avg_launch_s": t, "tensor_pipe_floor_s": mma_floor_s,
-                         "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}
+                         "tensor_pipe_floor_frac": mma_floor_s / t, "frac_of_fp32_fma_peak": flops / t / 1e12 / fp32_peak}
     else:
         out["update"] = {"kernel": f"update_kernel<{hd}> (gs_ppo_step, fp32 FMA pipe)", "bound": "tensor", "achieved": flops / t / 1e12,
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": traffic,

@@ -37,18 +37,22 @@
 //   W-b    [dW1 | db1][j][c] += sum_s dz1[s][j] x16[s][c]           (dW1[j][d] = col d + col 7+d, db1 = col 14)
 //
 // Schedule: one CTA per SM, 16 compute warps + one MMA-issuing warp per set.  A SET owns a 128-sample tile at a time and
-// two tile buffers P (h1, later dz1) and Q (h2, later dz2); thread = (sample row, 32-column group).  H = 64 runs TWO sets
+// two tile buffers P (h1) and Q (h2, then dz2, then dz1); thread = (sample row, 32-column group).  H = 64 runs TWO sets
 // on alternating tiles so that one set's SIMT stages overlap the other's MMA groups; H = 128 runs one set.  Per tile a set's
 // compute warps walk five stages, each gated by an MMA-completion mbarrier (tcgen05.commit) and closed by a per-warp arrive
 // on an operands-ready mbarrier (no CTA-wide barrier in the loop):
 //   A  z1 -> relu -> h1 (hi, lo) -> P            B  z2 -> relu -> h2 -> Q
 //   C  (one thread per row) out -> loss, metrics, g -> g16; cp.async of the next tile's record into X
-//   D  dh2 * act'(h2) -> dz2 -> Q  (after W-c released Q)      E  dh1 * act'(h1) -> dz1 -> P  (after W-a released P)
-// act' is re-derived from the tile being overwritten (relu: hi != 0), so nothing but two offsets lives across stages.
-// Weight-gradient accumulators stay in TMEM and are folded into the set's fp32 partial vector every 8 tiles (the tensor
-// core's accumulation truncates); partial vectors are summed in a fixed order by gs_update_finish -> deterministic gradients.
+//   D  dh2 * act'(h2) -> dz2 -> Q  (after W-c released Q)      E  dh1 * act'(h1 in P) -> dz1 -> Q  (after W-a released Q)
+// act' is re-derived from the activation still held in its tile (relu: hi != 0), so nothing but two offsets lives across stages.
+// The next tile's layer 1 is issued ahead of W-b, and W-b reads Q while stage A of the next tile already writes P.
+// Weight-gradient accumulators stay in TMEM for the whole launch (folded into the set's fp32 partial vector every 64 tiles: the
+// tensor core's accumulation truncates, but 28 tiles against a fold after every tile differ by 5e-6 of the gradient norm, measured;
+// a mid-kernel fold costs ~7,000 cycles because the partial vector has left L2 by then); partial vectors are summed in a fixed
+// order by gs_update_finish -> deterministic gradients.
 #include <type_traits>
 
+#define GS_FAST_TRANSCENDENTALS   // the loss stage is on the tile's critical path: ex2.approx / lg2.approx (2^-21 relative) instead of libm
 #include "mlp_tile.cuh"
 #include "tc_common.cuh"
 #include "update_shared.cuh"
@@ -62,12 +66,12 @@ namespace hfu {
 constexpr int kRows = 128;               // samples per tile == TMEM lanes
 constexpr uint32_t kSlab = 128 * 128;    // one [128][64] fp16 slab
 #ifndef GS_BF_FLUSH
-#define GS_BF_FLUSH 8
+#define GS_BF_FLUSH 64
 #endif
 constexpr int kFlushTiles = GS_BF_FLUSH;
 constexpr int kMaxD = 7;                 // x16 holds x_hi at 0.., x_lo at 7.., ones at 14, 15
 
-enum { BAR_Z1 = 0, BAR_Z2, BAR_OUT, BAR_DH2, BAR_WC, BAR_DH1, BAR_WA, BAR_END, RDY_X, RDY_H1, RDY_H2, RDY_G, RDY_DZ2, RDY_DZ1, kBars };
+enum { BAR_Z1 = 0, BAR_Z2, BAR_OUT, BAR_DH2, BAR_WC, BAR_DH1, BAR_WA, BAR_WB, RDY_X, RDY_H1, RDY_H2, RDY_G, RDY_DZ2, RDY_DZ1, kBars };
 
 template <int H>
 struct Cfg {
@@ -193,6 +197,19 @@ __global__ void batch_pack_kernel(BatchDev b, const uint32_t* __restrict__ offs,
     for (int q = 0; q < 4; ++q) packed[4 * pos + q] = rec[q];
 }
 
+// Development aid (build with GS_NVCC_EXTRA=-DGS_F16_TRACE): clock64() stamps of one tile of one CTA per set, compute warp 0 (role 0)
+// and the MMA warp (role 1); read back with gs_debug_f16_trace().  Not part of the ABI; absent from normal builds.
+#ifdef GS_F16_TRACE
+#ifndef GS_F16_TRACE_TILE
+#define GS_F16_TRACE_TILE 5
+#endif
+__device__ long long g_f16_trace[2][2][16];
+__device__ long long g_f16_tiles[2][64];   // tile start stamps of compute warp 0 of each set (slot 62: kernel entry, 63: exit)
+#define GS_TR(role, k) do { if (blockIdx.x == 7 && i == GS_F16_TRACE_TILE && lane == 0 && warp == ((role) == 1 ? C::kComputeWarps + set : set * C::kCW)) g_f16_trace[set][role][k] = clock64(); } while (0)
+#else
+#define GS_TR(role, k) do { } while (0)
+#endif
+
 template <int H, int ALGO, bool TRACK, int ACT>
 __global__ void __launch_bounds__(hfu::Cfg<H>::kThreads, 1)
 update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv_mom, const double* __restrict__ ret_mom,
@@ -210,6 +227,9 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int A = m.A, D = m.D;
+#ifdef GS_F16_TRACE
+    if (blockIdx.x == 7 && tid == 0) { g_f16_tiles[0][62] = clock64(); g_f16_tiles[1][62] = g_f16_tiles[0][62]; }
+#endif
 
     // ---- prologue that does not depend on the previous kernel's results ----------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -226,36 +246,44 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
     if (tid < PM_N) red[tid] = 0.0;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // programmatic dependent launch: the weights below come from the previous step
     // ---- weights -> operand tiles ----------------------------------------------------------------------------------------------
-    for (int i = tid; i < H * H / 2; i += C::kThreads) {
-        const int j = i / (H / 2), k = 2 * (i % (H / 2));
-        const float2 w = __ldg(reinterpret_cast<const float2*>(m.w2 + j * H + k));
-        uint32_t hi, lo;
-        split_pair(w.x, w.y, hi, lo);
+#pragma unroll 4
+    for (int i = tid; i < H * H / 4; i += C::kThreads) {      // independent 16-byte loads, several in flight per thread
+        const int j = i / (H / 4), k = 4 * (i % (H / 4));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(m.w2 + j * H) + (i % (H / 4)));
+        uint32_t h0, l0, h1, l1;
+        split_pair(w.x, w.y, h0, l0);
+        split_pair(w.z, w.w, h1, l1);
         const uint32_t o = tile_off(j, k, H);
-        *reinterpret_cast<uint32_t*>(sm + C::oW2hi + o) = hi;
-        *reinterpret_cast<uint32_t*>(sm + C::oW2lo + o) = lo;
+        *reinterpret_cast<uint2*>(sm + C::oW2hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(sm + C::oW2lo + o) = make_uint2(l0, l1);
     }
-    for (int i = tid; i < H * 64; i += C::kThreads) {
-        const int j = i >> 6, c = i & 63, g = c >> 4, e = c & 15;
-        float v = 0.f;
-        bool want_lo = false;
-        if (g == 0) {
-            if (e < 7) { if (e < D) v = __ldg(m.w1 + j * D + e); }
-            else if (e < 14) { if (e - 7 < D) v = __ldg(m.w1 + j * D + e - 7); }
-            else { v = __ldg(m.b1 + j); want_lo = e == 15; }
-        } else if (g == 1) {
-            if (e < D && e < 7) { v = __ldg(m.w1 + j * D + e); want_lo = true; }
-        } else if (g == 2) {
-            if (e >= 14) { v = __ldg(m.b2 + j); want_lo = e == 15; }
-        } else {
-            const int r = e & 3;
-            if (e < 12) {
-                v = r < A ? __ldg(m.wp + r * H + j) : ((r == A && m.has_value) ? __ldg(m.wv + j) : 0.f);
-                want_lo = e >= 8;
-            }
+    if (tid < H) {                                            // WS row j: every load of the row is independent -> one round trip
+        const int j = tid;
+        float w[kMaxD], whv[4];
+#pragma unroll
+        for (int d = 0; d < kMaxD; ++d) w[d] = d < D ? __ldg(m.w1 + j * D + d) : 0.f;
+        const float b1v = __ldg(m.b1 + j), b2v = __ldg(m.b2 + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) whv[r] = r < A ? __ldg(m.wp + r * H + j) : ((r == A && m.has_value) ? __ldg(m.wv + j) : 0.f);
+        uint32_t e[64];
+#pragma unroll
+        for (int q = 0; q < 64; ++q) e[q] = 0u;
+#pragma unroll
+        for (int d = 0; d < kMaxD; ++d) {
+            const uint32_t hi = f16_bits(w[d]);
+            e[d] = hi; e[7 + d] = hi; e[16 + d] = f16_bits(w[d] - f16_hi(w[d]));
         }
-        const uint32_t bits = want_lo ? f16_bits(v - f16_hi(v)) : f16_bits(v);
-        *reinterpret_cast<uint16_t*>(sm + C::oWS + tile_off(j, c, H)) = (uint16_t)bits;
+        e[14] = f16_bits(b1v); e[15] = f16_bits(b1v - f16_hi(b1v));
+        e[32 + 14] = f16_bits(b2v); e[32 + 15] = f16_bits(b2v - f16_hi(b2v));
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t hi = f16_bits(whv[r]);
+            e[48 + r] = hi; e[52 + r] = hi; e[56 + r] = f16_bits(whv[r] - f16_hi(whv[r]));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(sm + C::oWS + j * 128 + ((c ^ (j & 7)) << 4)) =
+                make_uint4(e[8 * c] | (e[8 * c + 1] << 16), e[8 * c + 2] | (e[8 * c + 3] << 16), e[8 * c + 4] | (e[8 * c + 5] << 16), e[8 * c + 6] | (e[8 * c + 7] << 16));
     }
     if (tid < 4) bhs[tid] = tid < A ? __ldg(m.bp + tid) : ((tid == A && m.has_value) ? __ldg(m.bv) : 0.f);
     if (tid == 0) {
@@ -287,19 +315,27 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         constexpr int KS = H / 16;                                                // k-steps over the feature dimension
         auto kfeat = [](int kk) -> uint32_t { return (uint32_t)(kk >> 2) * kSlab + (uint32_t)(kk & 3) * 32u; };          // activation tiles
         auto kw2 = [](int kk) -> uint32_t { return (uint32_t)(kk >> 2) * C::kW2Slab + (uint32_t)(kk & 3) * 32u; };       // W2 / WS rows = H
-#pragma unroll 1
-        for (int i = 0; i < n_my; ++i) {
-            const uint32_t p = (uint32_t)i & 1u;
-            const uint32_t sXg = sX + 32u * (1u + p);                             // x16 group of this tile
-            const uint32_t acc_w = (i % kFlushTiles) != 0 ? 1u : 0u;              // weight-gradient accumulators restart after a flush
-            if (i == 0) { mbar_wait(&bars[RDY_X], 0); fence_after_sync(); }
-            if (elect_one()) {                                                    // L1
+        auto issue_l1 = [&](int i) {                                              // z1(i) = x16(i) . [W1 | b1]: needs only the tile's record
+            const uint32_t sXg = sX + 32u * (1u + ((uint32_t)i & 1u));
+            if (elect_one()) {
                 mma_f16(T + C::cAcc0, desc(sXg), desc(sWS + 32u), idesc_f16(128, H, 0, 0), 0u);      // small terms first: the accumulator
                 mma_f16(T + C::cAcc0, desc(sXg), desc(sWS), idesc_f16(128, H, 0, 0), 1u);            // truncates relative to its magnitude
                 mma_commit(&bars[BAR_Z1]);
             }
             __syncwarp();
+        };
+        if (n_my > 0) {
+            mbar_wait(&bars[RDY_X], 0); fence_after_sync();
+            issue_l1(0);
+        }
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const uint32_t p = (uint32_t)i & 1u;
+            const uint32_t sXg = sX + 32u * (1u + p);                             // x16 group of this tile
+            const uint32_t acc_w = (i % kFlushTiles) != 0 ? 1u : 0u;              // weight-gradient accumulators restart after a flush
+            GS_TR(1, 1);
             mbar_wait(&bars[RDY_H1], p); fence_after_sync();
+            GS_TR(1, 2);
             if (elect_one()) {                                                    // bias + fwd
                 mma_f16(T + C::cAcc1, desc(sXg), desc(sWS + 64u), idesc_f16(128, H, 0, 0), 0u);
 #pragma unroll
@@ -311,7 +347,9 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
                 mma_commit(&bars[BAR_Z2]);
             }
             __syncwarp();
+            GS_TR(1, 3);
             mbar_wait(&bars[RDY_H2], p); fence_after_sync();
+            GS_TR(1, 4);
             if (elect_one()) {                                                    // heads: B = WS group 3 read MN-major (N = 16, K = feature rows)
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -323,7 +361,9 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
                 mma_commit(&bars[BAR_OUT]);
             }
             __syncwarp();
+            GS_TR(1, 5);
             mbar_wait(&bars[RDY_G], p); fence_after_sync();
+            GS_TR(1, 6);
             if (elect_one()) {
                 mma_f16(T + C::cAcc0, desc(sX), desc(sWS + 96u), idesc_f16(128, H, 0, 0), 0u);                   // dh2 = g16 . WS3
                 mma_commit(&bars[BAR_DH2]);
@@ -338,7 +378,9 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
                 mma_commit(&bars[BAR_WC]);
             }
             __syncwarp();
+            GS_TR(1, 7);
             mbar_wait(&bars[RDY_DZ2], p); fence_after_sync();
+            GS_TR(1, 8);
             if (elect_one()) {
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {                            // dgrad: B = W2 read MN-major (N = k, K = j rows)
@@ -359,19 +401,26 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
                 mma_commit(&bars[BAR_WA]);
             }
             __syncwarp();
+            if (i + 1 < n_my) {                                                   // the next tile's layer 1 goes ahead of this tile's last group:
+                mbar_wait(&bars[RDY_X], p ^ 1u); fence_after_sync();              // acc0 is free (dh2 was read in stage D), its record has landed
+                issue_l1(i + 1);
+            }
+            GS_TR(1, 9);
             mbar_wait(&bars[RDY_DZ1], p); fence_after_sync();
+            GS_TR(1, 10);
             if (elect_one()) {
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {                            // W-b: [dW1 | db1] += dz1^T x16
-                    const uint32_t a0 = pass == 0 ? sPlo : sPhi;
+                for (int pass = 0; pass < 2; ++pass) {                            // W-b: [dW1 | db1] += dz1^T x16   (dz1 lives in Q)
+                    const uint32_t a0 = pass == 0 ? sQlo : sQhi;
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
                         mma_f16(T + C::cW1, desc(a0 + (uint32_t)kk * 2048u, kSlab), desc(sXg + (uint32_t)kk * 2048u, kSlab), idesc_f16(H, 16, 1, 1),
                                  (pass | kk) ? 1u : acc_w);
                 }
-                if (i == n_my - 1) mma_commit(&bars[BAR_END]);
+                mma_commit(&bars[BAR_WB]);
             }
             __syncwarp();
+            GS_TR(1, 11);
         }
         return;
     }
@@ -427,21 +476,28 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         {
             float v[32];
             tmem_ld32(T + C::cW2 + 32 * cg, v);
-            tmem_ld_wait();
-            if (owner) {
-                float4* dst = reinterpret_cast<float4*>(out + po.w2 + (int64_t)mrow * H + 32 * cg);
-                const bool vec = (po.w2 & 3) == 0;
+            float* d1 = out + po.w2 + (int64_t)mrow * H + 32 * cg;
+            const bool vec = (po.w2 & 3) == 0;
+            float4 o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (owner && !first) {                            // every old value is requested before the first use: one L2 round trip
                 if (vec) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 o = first ? make_float4(0.f, 0.f, 0.f, 0.f) : dst[q];
-                        o.x = fmaf(v[4 * q], invB, o.x); o.y = fmaf(v[4 * q + 1], invB, o.y); o.z = fmaf(v[4 * q + 2], invB, o.z); o.w = fmaf(v[4 * q + 3], invB, o.w);
-                        dst[q] = o;
-                    }
+                    for (int q = 0; q < 8; ++q) o[q] = __ldcg(reinterpret_cast<const float4*>(d1) + q);
                 } else {
-                    float* d1 = out + po.w2 + (int64_t)mrow * H + 32 * cg;
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) d1[q] = first ? v[q] * invB : fmaf(v[q], invB, d1[q]);
+                    for (int q = 0; q < 8; ++q) o[q] = make_float4(__ldcg(d1 + 4 * q), __ldcg(d1 + 4 * q + 1), __ldcg(d1 + 4 * q + 2), __ldcg(d1 + 4 * q + 3));
+                }
+            }
+            tmem_ld_wait();
+            if (owner) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    o[q].x = fmaf(v[4 * q], invB, o[q].x); o[q].y = fmaf(v[4 * q + 1], invB, o[q].y);
+                    o[q].z = fmaf(v[4 * q + 2], invB, o[q].z); o[q].w = fmaf(v[4 * q + 3], invB, o[q].w);
+                    if (vec) reinterpret_cast<float4*>(d1)[q] = o[q];
+                    else { d1[4 * q] = o[q].x; d1[4 * q + 1] = o[q].y; d1[4 * q + 2] = o[q].z; d1[4 * q + 3] = o[q].w; }
                 }
             }
         }
@@ -450,16 +506,33 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
             tmem_ld16(T + C::cW2 + H, e);
             tmem_ld16(T + C::cW1, w1);
             tmem_ld16(T + C::cWh, wh);
+            // destinations of this row's 13 small entries: b2, w1[0..6], b1, wp[0..2], wv (unused ones point at b2: weight 0)
+            int64_t idx[13];
+            idx[0] = po.b2 + mrow;
+#pragma unroll
+            for (int d = 0; d < kMaxD; ++d) idx[1 + d] = d < D ? po.w1 + (int64_t)mrow * D + d : idx[0];
+            idx[8] = po.b1 + mrow;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) idx[9 + r] = r < A ? po.wp + (int64_t)r * H + mrow : idx[0];
+            idx[12] = m.has_value ? po.wv + mrow : idx[0];
+            float old[13];
+#pragma unroll
+            for (int q = 0; q < 13; ++q) old[q] = (owner && !first) ? __ldcg(out + idx[q]) : 0.f;
             tmem_ld_wait();
             if (owner) {
-                auto put = [&](int64_t idx, float val) { out[idx] = first ? val * invB : fmaf(val, invB, out[idx]); };
-                put(po.b2 + mrow, e[14]);
+                float val[13];
+                val[0] = e[14];
 #pragma unroll
-                for (int d = 0; d < kMaxD; ++d) if (d < D) put(po.w1 + (int64_t)mrow * D + d, w1[d] + w1[7 + d]);
-                put(po.b1 + mrow, w1[14]);
+                for (int d = 0; d < kMaxD; ++d) val[1 + d] = w1[d] + w1[7 + d];
+                val[8] = w1[14];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) if (r < A) put(po.wp + (int64_t)r * H + mrow, wh[r] + wh[4 + r]);
-                if (m.has_value) put(po.wv + mrow, A == 2 ? wh[2] + wh[6] : wh[3] + wh[7]);
+                for (int r = 0; r < 3; ++r) val[9 + r] = wh[r] + wh[4 + r];
+                val[12] = A == 2 ? wh[2] + wh[6] : wh[3] + wh[7];
+#pragma unroll
+                for (int q = 12; q >= 0; --q) {               // q = 0 (b2) last: the unused slots alias it
+                    const bool used = q == 0 || q == 8 || (q >= 1 && q <= 7 && q - 1 < D) || (q >= 9 && q <= 11 && q - 9 < A) || (q == 12 && m.has_value);
+                    if (used) out[idx[q]] = fmaf(val[q], invB, old[q]);
+                }
             }
         }
         fence_before_sync();
@@ -472,7 +545,8 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         if (lane == 0) mbar_arrive(&bars[which]);
     };
     // forward stage: 32 pre-activations of the row -> activation -> (hi, lo) -> tile
-    auto fwd_stage = [&](uint32_t acc_col, unsigned char* t_hi, unsigned char* t_lo, bool valid, float& zs, float& zq, uint32_t& dcnt) {
+    auto fwd_stage = [&](uint32_t acc_col, unsigned char* t_hi, unsigned char* t_lo, bool valid, float& zs, float& zq, uint32_t& dcnt,
+                         uint64_t* release, uint32_t parity) {
         float z[32];
         tmem_ld32(T + acc_col + 32 * cg, z);
         tmem_ld_wait();
@@ -490,19 +564,21 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
                 }
             }
         }
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split_pair(act_fwd(z[2 * e], ACT), act_fwd(z[2 * e + 1], ACT), hw[e], lw[e]);
+        if (release) mbar_wait(release, parity);              // the MMAs still reading the tile's previous content
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_pair(act_fwd(z[8 * c + 2 * e], ACT), act_fwd(z[8 * c + 2 * e + 1], ACT), hw[e], lw[e]);
             const uint32_t o = my_off + (uint32_t)(((c0 + c) ^ sw) << 4);
-            *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(t_lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+            *reinterpret_cast<uint4*>(t_lo + o) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
         }
     };
     // backward stage: d(loss)/d(activation) of the row * act'(activation held in the tile) -> (hi, lo) -> the same tile, once
     // `release` says the MMAs still reading the tile are done
-    auto bwd_stage = [&](uint32_t acc_col, unsigned char* t_hi, unsigned char* t_lo, uint64_t* release, uint32_t parity) {
+    auto bwd_stage = [&](uint32_t acc_col, const unsigned char* t_hi, const unsigned char* t_lo, unsigned char* d_hi, unsigned char* d_lo,
+                         uint64_t* release, uint32_t parity) {
         float d[32];
         tmem_ld32(T + acc_col + 32 * cg, d);
         uint4 hq[4];
@@ -542,8 +618,8 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint32_t o = my_off + (uint32_t)(((c0 + c) ^ sw) << 4);
-            *reinterpret_cast<uint4*>(t_hi + o) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
-            *reinterpret_cast<uint4*>(t_lo + o) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+            *reinterpret_cast<uint4*>(d_hi + o) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+            *reinterpret_cast<uint4*>(d_lo + o) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
         }
     };
 
@@ -556,6 +632,10 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         next_off = offset_of(1, next_ok);
         cp_async_wait_all();
         fence_proxy_async();
+        // Two sets that start together stay in lockstep (both in a SIMT stage, then both queueing MMAs: measured, clock64 trace): the
+        // second set starts half a tile late -- when the first set's head outputs are done -- so one set's MMA groups run under the
+        // other's SIMT stages, and that offset is self-sustaining.
+        if (C::kSets == 2 && set == 1) mbar_wait(&bars_all[BAR_OUT], 0);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[RDY_X]);
     }
@@ -567,20 +647,33 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         const uint32_t p = (uint32_t)i & 1u;
         const bool valid = tile_of(i) * kRows + row < b.n;
         // ---- A: h1 ----------------------------------------------------------------------------------------------------------
+#ifdef GS_F16_TRACE
+        if (blockIdx.x == 7 && lane == 0 && ws == 0 && i < 62) g_f16_tiles[set][i] = clock64();
+#endif
+        GS_TR(0, 0);
         mbar_wait(&bars[BAR_Z1], p);
         fence_after_sync();
-        if (i > 0 && (i % kFlushTiles) == 0) flush(i == kFlushTiles);
-        fwd_stage(C::cAcc0, S + C::oPhi, S + C::oPlo, valid, zs0, zq0, dead0);
+        GS_TR(0, 1);
+        if (i > 0 && (i % kFlushTiles) == 0) {               // every weight-gradient MMA of the previous tiles has completed
+            mbar_wait(&bars[BAR_WB], p ^ 1u);
+            fence_after_sync();
+            flush(i == kFlushTiles);
+        }
+        fwd_stage(C::cAcc0, S + C::oPhi, S + C::oPlo, valid, zs0, zq0, dead0, nullptr, 0u);   // P is free: W-a(i-1) was awaited in stage E
         warp_ready(RDY_H1);
         // ---- B: h2 ----------------------------------------------------------------------------------------------------------
+        GS_TR(0, 2);
         mbar_wait(&bars[BAR_Z2], p);
         fence_after_sync();
-        fwd_stage(C::cAcc1, S + C::oQhi, S + C::oQlo, valid, zs1, zq1, dead1);
+        GS_TR(0, 3);
+        fwd_stage(C::cAcc1, S + C::oQhi, S + C::oQlo, valid, zs1, zq1, dead1, i > 0 ? &bars[BAR_WB] : nullptr, p ^ 1u);   // W-b(i-1) reads dz1 from Q
         warp_ready(RDY_H2);
         // ---- C: loss (one thread per row) ----------------------------------------------------------------------------------------
+        GS_TR(0, 4);
         if (loss_thread) {
             mbar_wait(&bars[BAR_OUT], p);
             fence_after_sync();
+            GS_TR(0, 5);
             float c[16];
             tmem_ld16(T + C::cH, c);
             const uint4 sc = *reinterpret_cast<const uint4*>(Xrow + ((6 ^ sw) << 4));
@@ -606,19 +699,32 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
             warp_ready(RDY_G);
         }
         // ---- D: dz2 ---------------------------------------------------------------------------------------------------------
+        GS_TR(0, 6);
         mbar_wait(&bars[BAR_DH2], p);
         fence_after_sync();
-        bwd_stage(C::cAcc0, S + C::oQhi, S + C::oQlo, &bars[BAR_WC], p);
+        GS_TR(0, 7);
+        bwd_stage(C::cAcc0, S + C::oQhi, S + C::oQlo, S + C::oQhi, S + C::oQlo, &bars[BAR_WC], p);
         warp_ready(RDY_DZ2);
         // ---- E: dz1 ---------------------------------------------------------------------------------------------------------
+        if (loss_thread && i + 1 < n_my) {                    // the next tile's record (cp.async issued in stage C) has landed: its layer 1 may start
+            cp_async_wait_all();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[RDY_X]);
+        }
+        GS_TR(0, 8);
         mbar_wait(&bars[BAR_DH1], p);
         fence_after_sync();
-        bwd_stage(C::cAcc1, S + C::oPhi, S + C::oPlo, &bars[BAR_WA], p);
-        cp_async_wait_all();                                  // the next tile's record has landed (loss threads)
+        GS_TR(0, 9);
+        bwd_stage(C::cAcc1, S + C::oPhi, S + C::oPlo, S + C::oQhi, S + C::oQlo, &bars[BAR_WA], p);   // act'(h1) from P; dz1 -> Q once W-a is done with dz2
         warp_ready(RDY_DZ1);
+        GS_TR(0, 10);
     }
+#ifdef GS_F16_TRACE
+    if (blockIdx.x == 7 && lane == 0 && ws == 0) g_f16_tiles[set][61] = clock64();
+#endif
     if (n_my > 0) {
-        mbar_wait(&bars[BAR_END], 0);
+        mbar_wait(&bars[BAR_WB], (uint32_t)(n_my - 1) & 1u);
         fence_after_sync();
         flush(n_my <= kFlushTiles);
     }
@@ -648,6 +754,9 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
         if (lane < A) out[po.bp + lane] = sgm * ncs[4];
         else if (lane == A && m.has_value) out[po.bv] = sgm * ncs[4];
     }
+#ifdef GS_F16_TRACE
+    if (blockIdx.x == 7 && lane == 0 && ws == 0) g_f16_tiles[set][63] = clock64();
+#endif
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -696,3 +805,12 @@ int launch_batch_pack(const BatchDev& b, const uint32_t* offs, void* packed, cud
 }
 
 }  // namespace gs
+
+#ifdef GS_F16_TRACE
+extern "C" int gs_debug_f16_trace(long long* host_out /* [2][2][16] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_f16_trace, sizeof(long long) * 64);
+}
+extern "C" int gs_debug_f16_tiles(long long* host_out /* [2][64] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_f16_tiles, sizeof(long long) * 128);
+}
+#endif

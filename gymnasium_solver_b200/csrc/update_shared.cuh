@@ -118,8 +118,8 @@ __device__ __forceinline__ void sample_loss(const float (&out)[kNH], int A, int 
     pm[PM_KL] += lp_old - logp;
     const float dlp = logp - lp_old;
     const float dcl = fminf(fmaxf(dlp, -20.f), 20.f);             // utils/torch.py:115-118
-    const float r2 = (ALGO == ALGO_PPO && dcl == dlp) ? ratio_ppo : expf(dcl);   // same argument as the surrogate's ratio: same bits
-    pm[PM_AKL] += (r2 - 1.f) - logf(r2);
+    const float r2 = (ALGO == ALGO_PPO && dcl == dlp) ? ratio_ppo : GS_EXPF(dcl);   // same argument as the surrogate's ratio: same bits
+    pm[PM_AKL] += (r2 - 1.f) - GS_LOGF(r2);
     pm[PM_COUNT] += 1.f;
 }
 

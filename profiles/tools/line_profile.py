@@ -28,6 +28,9 @@ for ln in sass:
 sel = ["--kernel-name", "regex:" + sys.argv[5], "--launch-count", "1"] if len(sys.argv) > 5 else []
 out = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+second = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(second) > 1:                      # several launches in the report: keep the first
+    rows = rows[:second[1]]
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 body = rows[2:]

@@ -41,6 +41,8 @@ names = np.array(names)
 for impl in (0, 1):
     N.lib().gs_set_update_impl(impl)
     g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, hp)
+    if impl == 0 and os.environ.get("GS_DEV_SAVE"):
+        np.save(os.environ["GS_DEV_SAVE"], g_raw)
     err = np.abs(g_raw - ref)
     print(f"impl {impl}: max|ref| {np.abs(ref).max():.3e}  L2 rel vs fp64 {np.linalg.norm(g_raw-ref)/np.linalg.norm(ref):.3e}  vs torch fp32 {np.linalg.norm(g_raw-ref32)/np.linalg.norm(ref32):.3e}  max abs err / max|ref| {np.abs(g_raw-ref).max()/np.abs(ref).max():.3e}")
     for k in P.PARAM_ORDER:

@@ -27,7 +27,10 @@ z = torch.randn(T, Nn, generator=g)
 dev = [E.cu(obs), E.cu(actions.int()), E.cu(z * 0.1 - 0.7), E.cu(z), E.cu(z + 0.3), E.cu(z * 2)]
 n = 1 << 20
 batch, keep = E.make_batch(T, Nn, *dev, n=n, perm_key=77, perm_offset=0, perm_len=T * Nn)
-hp = N.GsPpoHparams(); hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef, hp.normalize_adv, hp.track_activations = 0.2, 0.2, 0.5, 0.01, 1, 1
+if not os.environ.get("GS_DEV_UNPACKED"):
+    E.pack_rollout(batch, keep)      # as the agent does once per rollout: the kernel gathers 64-byte records
+hp_track = int(os.environ.get("GS_DEV_TRACK", "1"))
+hp = N.GsPpoHparams(); hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef, hp.normalize_adv, hp.track_activations = 0.2, 0.2, 0.5, 0.01, 1, hp_track
 m = N.mlp_struct_from_params(E.dev_params(p), "relu")
 Pn = N.lib().gs_mlp_param_count(C.byref(m))
 wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0, n)
