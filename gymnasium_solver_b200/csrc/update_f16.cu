@@ -773,9 +773,17 @@ static int launch_f16_h(const MlpDev& md, const BatchDev& b, const HpDev& hp, bo
     if (md.act == GS_ACT_RELU) kern = track ? update_f16_kernel<H, ALGO, true, GS_ACT_RELU> : update_f16_kernel<H, ALGO, false, GS_ACT_RELU>;
     else kern = track ? update_f16_kernel<H, ALGO, true, GS_ACT_TANH> : update_f16_kernel<H, ALGO, false, GS_ACT_TANH>;
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
-    kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(md, b, hp, adv_mom, ret_mom, offs, reinterpret_cast<const uint4*>(records), grad_partials, pstride,
-                                                   metric_partials, dead);
-    GS_LAUNCH_CHECK();
+    // Programmatic dependent launch: the CTAs may start while the previous kernel of the stream (the step tail of the previous
+    // minibatch, which triggers early) is still in its serial phase; everything up to griddepcontrol.wait -- TMEM allocation,
+    // barrier init, zeroing -- runs under it, the weights are read after it.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)C::kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GS_CUDA(cudaLaunchKernelEx(&cfg, kern, md, b, hp, adv_mom, ret_mom, offs, reinterpret_cast<const uint4*>(records), grad_partials, pstride,
+                               metric_partials, dead));
     return 0;
 }
 

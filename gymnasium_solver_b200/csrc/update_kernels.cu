@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     __shared__ int is_last;
     const int tid = threadIdx.x;
     const int phase = (int)(peer.epoch & 1u);
+    // programmatic dependent launch: the next minibatch's update kernel may be scheduled now; it runs its weight-independent
+    // prologue and then blocks in griddepcontrol.wait until this grid has completed and flushed (parameters, moments, ticket)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- phase A (every block): sum of the per-CTA partial vectors in a fixed order (16 contiguous groups of CTAs, then the
     //      groups in order); the result goes to grads (one rank) or straight into every rank's receive slot over NVLink
     //      (posted P2P stores, no reads cross the link)

@@ -16,7 +16,10 @@ CASES = [("C3 CartPole-v1:reinforce_b200", "CartPole-v1", "reinforce_b200", 3),
          ("C4 Acrobot-v1:ppo_b200", "Acrobot-v1", "ppo_b200", 1),
          ("C4 MountainCar-v0:ppo_b200", "MountainCar-v0", "ppo_b200", 1)]
 print("| config | envs x steps | network | passes x minibatches | ms per iteration | env-steps/s | update path |\n|---|---|---|---|---|---|---|")
+only = os.environ.get("GS_CASES")
 for name, env, variant, iters in CASES:
+    if only and not any(o in name for o in only.split(",")):
+        continue
     cfg = load_config(env, variant)
     cfg.eval_freq_epochs = None
     cfg.validate()
@@ -33,7 +36,7 @@ for name, env, variant, iters in CASES:
     steps = int(cfg.n_envs) * int(cfg.n_steps)
     n_mb = steps // int(cfg.batch_size)
     hd = tuple(cfg.hidden_dims)
-    path = "tcgen05 (3xTF32)" if hd == (64, 64) else "fp32 FMA pipe"
+    path = "tcgen05 (fp16x3)" if hd in ((64, 64), (128, 128)) else "fp32 FMA pipe"
     print(f"| {name} | {int(cfg.n_envs):,} x {int(cfg.n_steps)} | {hd} | {int(agent.n_epochs)} x {n_mb} | {ms:.1f} | {steps / ms * 1e3 / 1e6:.1f} M | {path} |", flush=True)
     del agent
     torch.cuda.empty_cache()
