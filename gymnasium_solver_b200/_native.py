@@ -110,6 +110,7 @@ SIGNATURES = {
     "gs_valid_index_map": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gs_valid_index_map_workspace_bytes": (_i64, [_i64]),
     "gs_moments": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "gs_moments_valid": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "gs_normalize": (_i32, [_vp, _i64, _vp, _f32, _vp, _vp]),
     "gs_shift_by_mean": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "gs_batch_moments": (_i32, [C.POINTER(GsBatch), _vp, _vp, _vp]),

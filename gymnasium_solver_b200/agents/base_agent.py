@@ -34,6 +34,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as N
+from ..utils import distributed as D
 from ..utils.distributed import PeerGroup, allreduce_moments, average_gradients, shard_spec
 from ..utils.environment import build_env_from_config
 from ..utils.optimizer_factory import EngineAdam, build_optimizer
@@ -634,6 +635,12 @@ class BaseAgent(nn.Module):
                 if log_fn is not None and self.rank == 0:
                     log_fn(row)
                 self.current_epoch += 1
+                # every rank evaluates its own env shard: the stop decision is taken together (any rank over the threshold stops all),
+                # the budget / max_epochs exits above are functions of the global step count and already identical everywhere
+                if self.world_size > 1 and (cfg.early_stop_on_train_threshold or cfg.early_stop_on_eval_threshold):
+                    self.should_stop = D.agree_any(self.should_stop, self.device, self.world_size)
+                    if self.should_stop and not reason:
+                        reason = "another rank crossed the early-stopping threshold"
                 if self.should_stop:
                     break
         except BaseException as exc:
@@ -834,7 +841,10 @@ class BaseAgent(nn.Module):
             config = dataclasses.asdict(self.config) if dataclasses.is_dataclass(self.config) else dict(vars(self.config))
             config["algo_id"] = self.config.algo_id
             np_state = np.random.get_state()
-            state = {"epoch": int(self.current_epoch), "total_env_steps": col.total_steps, "total_vec_steps": col.total_vec_steps,
+            # total_env_steps is the GLOBAL count (what the budget, the schedules and the logged metric use); per_rank_* restore this
+            # rank layout's collector counters exactly
+            state = {"epoch": int(self.current_epoch), "total_env_steps": col.total_steps * self.world_size, "total_vec_steps": col.total_vec_steps,
+                     "per_rank_env_steps": col.total_steps,
                      "run_id": getattr(getattr(self, "run", None), "run_id", None), "config": config,
                      "best_train_reward": finite(col._best_episode_reward),
                      "best_val_reward": finite(self.get_rollout_collector("val")._best_episode_reward),
@@ -850,7 +860,10 @@ class BaseAgent(nn.Module):
         env = self.get_env("train")
         torch.save({"snapshot": env.snapshot().cpu(), "obs": None if col.obs is None else col.obs.cpu(),
                     "stats": None if col._stats_dev is None else col._stats_dev.cpu(), "n_envs": env.num_envs,
-                    "env_id_offset": self.shard.env_id_offset}, d / f"env_state.rank{self.rank}.pt")
+                    "env_id_offset": self.shard.env_id_offset,
+                    # stamp: a shard is only an exact resume point next to the weights of the same save
+                    "epoch": int(self.current_epoch), "total_vec_steps": int(col.total_vec_steps), "world_size": self.world_size},
+                   d / f"env_state.rank{self.rank}.pt")
 
     def _load_model_state(self, state_dict, strict: bool) -> None:
         """reference agents/base_agent.py:754-781: strict load, or (transfer learning) only the tensors whose key and shape match."""
@@ -898,7 +911,9 @@ class BaseAgent(nn.Module):
             random.setstate((rs["random"][0], tuple(rs["random"][1]), rs["random"][2]))
         col = self.get_rollout_collector("train")
         self.current_epoch = int(state.get("epoch", 0))
-        col.total_steps = int(state.get("total_env_steps", state.get("total_timesteps", 0)))
+        # the collector counts this rank's steps; state.json holds the global count (the reference's field, and what a checkpoint
+        # written under another world size must be read as)
+        col.total_steps = int(state.get("total_env_steps", state.get("total_timesteps", 0))) // self.world_size
         col.total_vec_steps = int(state.get("total_vec_steps", 0))
         best_train = state.get("best_train_reward", state.get("best_episode_reward"))
         if best_train is not None:
@@ -910,6 +925,12 @@ class BaseAgent(nn.Module):
         shard = d / f"env_state.rank{self.rank}.pt"
         if shard.exists() and int(state.get("world_size", 1)) == self.world_size:      # same sharding: continue bit for bit
             es = torch.load(shard, map_location="cpu")
+            stamped = "epoch" in es
+            if stamped and (int(es["epoch"]) != int(state.get("epoch", -1)) or int(es["total_vec_steps"]) != int(state.get("total_vec_steps", -1))):
+                # a shard of another save (ranks once disagreed on when to checkpoint): weights and env state would not belong together
+                if self.rank == 0:
+                    print(f"Ignoring {shard.name}: written at epoch {es['epoch']}, state.json is epoch {state.get('epoch')}")
+                es = {"obs": None}
             if es["obs"] is not None:
                 col._sync_device_and_prepare_buffers()
                 self.get_env("train").restore(es["snapshot"])

@@ -191,7 +191,8 @@ __global__ void valid_apply_kernel(const int32_t* __restrict__ last_terminal, co
         } else {
             const int32_t pe = max(inc[e], block_prefix[e >> 10]);
             if (pe >= 0) target = (int64_t)pe * T + last_terminal[pe];
-            else target = fe < 0x7fffffff ? (int64_t)fe * T : 0;   // prefix before the first valid entry -> first valid
+            else target = fe < 0x7fffffff ? (int64_t)fe * T : i;   // prefix before the first valid entry -> first valid; NO valid entry at
+                                                                   // all -> identity (the reference returns (None, None) and does not remap)
         }
         if (valid_mask) valid_mask[i] = valid;
         idx_map[i] = target;
@@ -201,8 +202,9 @@ __global__ void valid_init_kernel(unsigned long long* n_valid, int32_t* first_en
 
 // ---- moments / normalise ------------------------------------------------------------------------------------------------
 __global__ void moments_kernel(const float* __restrict__ x, const int32_t* __restrict__ last_terminal, int T, int64_t N,
-                               double* __restrict__ out) {
+                               double* __restrict__ out, const int64_t* __restrict__ n_valid) {
     __shared__ double scratch[32];
+    if (n_valid && *n_valid == 0) last_terminal = nullptr;   // no valid entry: the reference's mask is None and the statistics cover every element
     double s = 0.0, s2 = 0.0, c = 0.0;
     const int64_t total = N * (int64_t)T;
     const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -249,8 +251,8 @@ __global__ void moments_kernel(const float* __restrict__ x, const int32_t* __res
     if (threadIdx.x == 0 && c > 0.0) { atomicAdd(out, s); atomicAdd(out + 1, s2); atomicAdd(out + 2, c); }
 }
 
-__global__ void normalize_kernel(const float* __restrict__ x, int64_t n, const double* __restrict__ mom, float eps, int mode,
-                                 float* __restrict__ y) {
+// x == y (in place) is allowed and used by the collector: no __restrict__ on the two
+__global__ void normalize_kernel(const float* x, int64_t n, const double* __restrict__ mom, float eps, int mode, float* y) {
     const double cnt = mom[2] > 0.0 ? mom[2] : 1.0;
     const double mu = mom[0] / cnt;
     double var = mom[1] / cnt - mu * mu;   // population variance (numpy .std())
@@ -343,7 +345,21 @@ int gs_moments(const float* x, const int32_t* last_terminal, int T, int64_t N, d
     int64_t blocks = (total + 1023) / 1024;
     const int64_t cap = 8ll * sm_count(device);
     if (blocks > cap) blocks = cap;
-    moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, last_terminal, T, N, out);
+    moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, last_terminal, T, N, out, nullptr);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_moments_valid(const float* x, const int32_t* last_terminal, const int64_t* n_valid, int T, int64_t N, double* out, void* stream) {
+    if (!x || !out || !last_terminal || !n_valid) GS_FAIL("gs_moments_valid: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_moments_valid: empty input");
+    int device = 0;
+    GS_CUDA(cudaGetDevice(&device));
+    const int64_t total = N * (int64_t)T;
+    int64_t blocks = (total + 1023) / 1024;
+    const int64_t cap = 8ll * sm_count(device);
+    if (blocks > cap) blocks = cap;
+    moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, last_terminal, T, N, out, n_valid);
     GS_LAUNCH_CHECK();
     return 0;
 }

@@ -127,6 +127,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"((uint32_t)GS_MBAR_HINT_NS)
             : "memory");
         if (done) return;
+#ifdef GS_MBAR_BACKOFF_NS
+        __nanosleep(GS_MBAR_BACKOFF_NS);
+#endif
     }
     __trap();
 }

@@ -679,6 +679,7 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
             const uint4 sc = *reinterpret_cast<const uint4*>(Xrow + ((6 ^ sw) << 4));
             const float ret_s = *reinterpret_cast<const float*>(Xrow + ((7 ^ sw) << 4));
             tmem_ld_wait();
+            GS_TR(0, 11);
             float g[kNH] = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 float outv[kNH];
@@ -689,14 +690,18 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
 #pragma unroll
                 for (int r = 0; r < kNH; ++r) gsum[r] += g[r];
             }
+            GS_TR(0, 12);
             uint32_t h01, l01, h23, l23;
             split_pair(g[0], g[1], h01, l01);
             split_pair(g[2], g[3], h23, l23);
             *reinterpret_cast<uint4*>(Xrow + ((0 ^ sw) << 4)) = make_uint4(h01, h23, l01, l23);
             *reinterpret_cast<uint4*>(Xrow + ((1 ^ sw) << 4)) = make_uint4(h01, h23, 0u, kOnes2);
+            GS_TR(0, 13);
             if (i + 1 < n_my) prefetch(i + 1, next_off, next_ok);   // the scalars above were consumed: their slot may be overwritten
+            GS_TR(0, 14);
             next_off = offset_of(i + 2, next_ok);
             warp_ready(RDY_G);
+            GS_TR(0, 15);
         }
         // ---- D: dz2 ---------------------------------------------------------------------------------------------------------
         GS_TR(0, 6);

@@ -82,6 +82,9 @@ class Trainer:
                     agent.validation_epoch()
                     self._call("on_validation_epoch_end", agent)
                 agent.current_epoch += 1
+                if getattr(agent, "world_size", 1) > 1:         # callbacks judged rank-local metrics: leave the lock-step loop together
+                    from .utils import distributed as D
+                    self.should_stop = D.agree_any(self.should_stop, agent.device, agent.world_size)
         except BaseException as exc:                        # Lightning's on_exception: callbacks, then the module (joins a background evaluation)
             self._call("on_exception", agent, exc)
             if hasattr(agent, "on_exception"):
@@ -199,8 +202,14 @@ class ModelCheckpointCallback(Callback):
         if self.metric not in trainer.logged_metrics:
             return
         value = float(trainer.logged_metrics[self.metric])
+        world = getattr(pl_module, "world_size", 1)
+        stopping = trainer.should_stop
+        if world > 1:                                           # save_checkpoint is collective (every rank writes its env shard): one decision
+            from .utils import distributed as D
+            value = D.broadcast_value(value, pl_module.device, world)
+            stopping = D.agree_any(stopping, pl_module.device, world)
         is_best = value > self.best_value if self.mode == "max" else value < self.best_value
-        if not (self.first_eval or is_best or trainer.should_stop):
+        if not (self.first_eval or is_best or stopping):
             return
         mark_best = is_best or self.first_eval
         if mark_best:

@@ -117,3 +117,31 @@ def max_over_ranks(value: float, device, world_size: int) -> float:
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _collective_device(device):
+    """Tensors of control-plane collectives live where the default group's backend can reduce them."""
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return device
+    return torch.device("cpu")
+
+
+def agree_any(flag: bool, device, world_size: int) -> bool:
+    """True on EVERY rank as soon as one rank raises the flag (MAX all-reduce).  Ranks evaluate their own env shard, so a threshold
+    on a rank-local mean is crossed at different epochs; every exit of the lock-step training loop has to be taken by all ranks
+    together, or the ranks that continue wait forever for the one that left (gs_update_finish spins on its NVLink flag)."""
+    if world_size <= 1 or not (dist.is_available() and dist.is_initialized()):
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=_collective_device(device))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+
+
+def broadcast_value(value: float, device, world_size: int, src: int = 0) -> float:
+    """Rank ``src``'s value on every rank: decisions that must be identical everywhere (is this evaluation the best so far?)
+    are derived from one rank's metric."""
+    if world_size <= 1 or not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_collective_device(device))
+    dist.broadcast(t, src=src)
+    return float(t.item())

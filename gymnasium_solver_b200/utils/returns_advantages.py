@@ -107,12 +107,17 @@ def valid_mask_and_index_map_from_last_terminal(last_terminal: torch.Tensor, T: 
     return mask, imap, n_valid
 
 
-def moments_into(x: torch.Tensor, out: torch.Tensor, last_terminal: Optional[torch.Tensor] = None) -> None:
-    """out[0:3] += (sum, sumsq, count) of a (T, N) device array (optionally only t <= last_terminal[n])."""
+def moments_into(x: torch.Tensor, out: torch.Tensor, last_terminal: Optional[torch.Tensor] = None, n_valid: Optional[torch.Tensor] = None) -> None:
+    """out[0:3] += (sum, sumsq, count) of a (T, N) device array (optionally only t <= last_terminal[n]).  With ``n_valid`` (the
+    device count gs_valid_index_map wrote) a rollout without any valid entry is counted in full, like the reference's None mask
+    (rollout_collector.py:435-455)."""
     T = x.shape[0]
     n = x.numel() // T
     with torch.cuda.device(x.device):
-        N.check(N.lib().gs_moments(N.ptr(x), N.ptr(last_terminal), T, n, N.ptr(out), N.stream()))
+        if last_terminal is not None and n_valid is not None:
+            N.check(N.lib().gs_moments_valid(N.ptr(x), N.ptr(last_terminal), N.ptr(n_valid), T, n, N.ptr(out), N.stream()))
+        else:
+            N.check(N.lib().gs_moments(N.ptr(x), N.ptr(last_terminal), T, n, N.ptr(out), N.stream()))
 
 
 def _normalize(x, eps: float = 1e-8):

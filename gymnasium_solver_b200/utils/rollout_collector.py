@@ -299,7 +299,7 @@ class RolloutCollector:
         T, n = end - start, self.n_envs
         sl = slice(start, end)
         adv, ret = self._adv[sl], self._ret[sl]
-        valid_lt = None
+        valid_lt = n_valid = None
         with torch.cuda.device(self.device):
             st = N.stream()
             if self.returns_type == "gae:rtg" and self.advantages_type == "gae":
@@ -326,13 +326,14 @@ class RolloutCollector:
                 mom = self._scratch_mom[0].zero_()
                 moments_into(ret, mom)
                 N.check(L.gs_normalize(N.ptr(ret), ret.numel(), N.ptr(mom), 1e-8, N.ptr(ret), st))
-            moments_into(adv, self._stat_row("adv"), valid_lt)
+            # valid positions only; a rollout WITHOUT any real terminal has no mask in the reference and counts in full (n_valid == 0)
+            moments_into(adv, self._stat_row("adv"), valid_lt, n_valid)
             if self.normalize_advantages:
                 mom = self._scratch_mom[1].zero_()
                 moments_into(adv, mom)
                 N.check(L.gs_normalize(N.ptr(adv), adv.numel(), N.ptr(mom), 1e-8, N.ptr(adv), st))
-                moments_into(adv, self._stat_row("adv_norm"), valid_lt)
-            moments_into(ret, self._stat_row("ret"), valid_lt)
+                moments_into(adv, self._stat_row("adv_norm"), valid_lt, n_valid)
+            moments_into(ret, self._stat_row("ret"), valid_lt, n_valid)
         return adv, ret
 
     # ------------------------------------------------------------------------------------------------ evaluation

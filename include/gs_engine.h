@@ -254,6 +254,9 @@ int64_t gs_valid_index_map_workspace_bytes(int64_t N);
  * when given only t <= last_terminal[n] contributes (RunningStats over valid returns, rollout_collector.py:415-418).
  * Accumulates INTO out (caller zeroes). */
 int gs_moments(const float* x, const int32_t* last_terminal, int T, int64_t N, double* out, void* stream);
+/* The same over the valid entries of a rollout, with the reference's fallback: when n_valid (device int64[1], written by
+ * gs_valid_index_map) is 0 the mask is None there and the statistics cover EVERY element (rollout_collector.py:435-455). */
+int gs_moments_valid(const float* x, const int32_t* last_terminal, const int64_t* n_valid, int T, int64_t N, double* out, void* stream);
 /* y = (x - mean)/(std + eps) with mean/std derived on device from moments (population std, numpy semantics,
  * returns_advantages.py:55-64); in place allowed. */
 int gs_normalize(const float* x, int64_t n, const double* moments, float eps, float* y, void* stream);

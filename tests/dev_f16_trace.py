@@ -9,7 +9,7 @@ import ctypes as C
 buf = (C.c_longlong * 64)()
 rc = C.CDLL(N.LIB_PATH).gs_debug_f16_trace(buf)
 v = list(buf)
-names0 = ["A:wait z1", "A:start", "B:wait z2", "B:start", "C:enter", "C:start(loss)", "D:wait dh2", "D:start", "E:wait dh1", "E:start", "E:done"]
+names0 = ["A:wait z1", "A:start", "B:wait z2", "B:start", "C:enter", "C:start(loss)", "D:wait dh2", "D:start", "E:wait dh1", "E:start", "E:done", "C:ld done", "C:loss done", "C:g16 stored", "C:prefetch issued", "C:ready"]
 names1 = ["L1 issue", "L1 issued", "fwd go", "fwd issued", "heads go", "heads issued", "dh2/Wc go", "issued", "dgrad/Wa go", "issued", "Wb go", "Wb issued"]
 for s in range(2):
     base = v[s * 32]

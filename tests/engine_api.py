@@ -70,6 +70,23 @@ def moments(x, last_terminal=None):
     return out.cpu().numpy()
 
 
+def moments_valid(x, last_terminal):
+    """gs_valid_index_map's n_valid + gs_moments_valid: masked moments, or all elements when the rollout has no valid entry."""
+    xt = cu(x, torch.float32)
+    T, Nn = xt.shape
+    lt = cu(last_terminal, torch.int32)
+    mask = torch.empty(Nn * T, dtype=torch.uint8, device=DEV)
+    imap = torch.empty(Nn * T, dtype=torch.int64, device=DEV)
+    nv = torch.zeros(1, dtype=torch.int64, device=DEV)
+    wsb = N.lib().gs_valid_index_map_workspace_bytes(Nn)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    N.check(N.lib().gs_valid_index_map(N.ptr(lt), T, Nn, N.ptr(mask), N.ptr(imap), N.ptr(nv), N.ptr(ws), wsb, N.stream()))
+    out = torch.zeros(3, dtype=torch.float64, device=DEV)
+    N.check(N.lib().gs_moments_valid(N.ptr(xt), N.ptr(lt), N.ptr(nv), T, Nn, N.ptr(out), N.stream()))
+    sync()
+    return out.cpu().numpy()
+
+
 def normalize(x, eps=1e-8, shift_only=False):
     xt = cu(x, torch.float32)
     T, Nn = xt.shape

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gymnasium_solver_b200.utils.distributed import allreduce_moments, average_gradients, exchange_handles, max_over_ranks, shard_spec
+from gymnasium_solver_b200.utils.distributed import (agree_any, allreduce_moments, average_gradients, broadcast_value, exchange_handles,
+                                                      max_over_ranks, shard_spec)
 
 
 def test_shard_spec_partitions_envs_and_batches():
@@ -40,6 +41,10 @@ def _worker(rank, world, port, out):
         # the 64-byte IPC handles of the NVLink peer group travel through the same process group, concatenated in rank order
         handles = exchange_handles(bytes([rank + 1]) * 64, world, torch.device("cpu"))
         assert handles == b"".join(bytes([r + 1]) * 64 for r in range(world))
+        # lock-step exits: a stop decision only one rank reached is taken by all; a checkpoint decision follows rank 0's metric
+        stop_seq = [agree_any(rank == 1 and epoch == 3, torch.device("cpu"), world) for epoch in range(5)]
+        assert stop_seq == [False, False, False, True, False]
+        assert broadcast_value(10.0 + rank, torch.device("cpu"), world) == 10.0
         out.put((rank, local.numpy(), grads.numpy(), x.numpy(), mom.numpy(), t))
     finally:
         dist.destroy_process_group()
@@ -91,3 +96,8 @@ def test_keyed_bijection_mirror_is_a_permutation_and_mixes():
         for k in range(8):
             counts[k] = torch.bincount((p[k * n // 8:(k + 1) * n // 8] * 8 // n), minlength=8).float()
         assert float((counts / (n / 64) - 1).abs().max()) < 0.15
+
+
+def test_stop_agreement_is_a_no_op_for_one_rank():
+    assert agree_any(True, torch.device("cpu"), 1) is True and agree_any(False, torch.device("cpu"), 1) is False
+    assert broadcast_value(3.5, torch.device("cpu"), 1) == 3.5

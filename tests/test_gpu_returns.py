@@ -108,8 +108,17 @@ def test_valid_map_reference_known_answers_and_sparse_terminals():
     np.testing.assert_array_equal(mask, [1, 1, 0, 0, 0, 0, 0, 0, 0, 0])
     np.testing.assert_array_equal(imap, [0, 1, 1, 1, 1, 1, 1, 1, 1, 1])
     assert nv == 2
-    # no terminal at all -> n_valid == 0 (reference returns None)
-    assert E.valid_index_map(np.full(7, -1, np.int32), 4)[2] == 0
+    # no terminal at all -> n_valid == 0; the reference returns (None, None) and trains on every sample WITHOUT a remap
+    # (returns_advantages.py:49-50): the map must be the identity, not "everything -> sample 0"
+    mask, imap, nv = E.valid_index_map(np.full(7, -1, np.int32), 4)
+    assert nv == 0 and not mask.any()
+    np.testing.assert_array_equal(imap, np.arange(28))
+    # ... and the rollout's running statistics then cover every element (rollout_collector.py:435-455), the baseline none
+    x = np.arange(28, dtype=np.float32).reshape(4, 7)
+    np.testing.assert_allclose(E.moments_valid(x, np.full(7, -1, np.int32)), [x.sum(), (x.astype(np.float64) ** 2).sum(), 28])
+    np.testing.assert_allclose(E.moments(x, np.full(7, -1, np.int32)), [0, 0, 0])
+    lt = np.array([2, -1, 0, -1, -1, -1, -1], np.int32)
+    np.testing.assert_allclose(E.moments_valid(x, lt), E.moments(x, lt))
     # long runs of envs without terminals, crossing the 1024-env scan blocks
     N, T = 5000, 6
     rng = np.random.default_rng(0)
