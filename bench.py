@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE_PASS = {(64, 64): 27264, (256, 256): 403968}   # 3 x forward flops
-GAE_BYTES_PER_ELEM = 22                                           # 18 B/elem + 4 B/elem dense bootstrapped array
+GAE_BYTES_PER_ELEM = 18                                           # v 4 + r 4 + done 1 + timeout 1 read, adv 4 + ret 4 written (the all-zero bootstrap array is not read)
 
 
 def _peaks():
@@ -309,12 +309,12 @@ def kernel_rooflines(agent, cfg, dev):
     adv, ret = torch.empty_like(b.rewards_buf), torch.empty_like(b.rewards_buf)
 
     def one_gae():
-        N.check(N.lib().gs_gae(N.ptr(b.values_buf), N.ptr(b.rewards_buf), N.ptr(b.dones_buf), N.ptr(b.timeouts_buf), N.ptr(col._last_values),
-                               N.ptr(b.bootstrapped_values_buf), T, n, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.stream()))
+        N.check(N.lib().gs_gae_zero_boot(N.ptr(b.values_buf), N.ptr(b.rewards_buf), N.ptr(b.dones_buf), N.ptr(b.timeouts_buf), N.ptr(col._last_values),
+                                         T, n, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.stream()))
 
     t = timed(one_gae)
     gbytes = GAE_BYTES_PER_ELEM * T * n
-    out["gae"] = {"kernel": "gae_kernel<HAS_BOOT>", "bound": "hbm", "achieved": gbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    out["gae"] = {"kernel": "gae_kernel<zero bootstrap> (the collector's call: gs_gae_zero_boot)", "bound": "hbm", "achieved": gbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": gbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": tr("gae_kernel"), "algorithmic_bytes_per_launch": gbytes, "avg_launch_s": t}
 
     # fused collect kernel: 34 B/sample store traffic is the algorithmic HBM figure; it is compute (fp32 MLP + fp64 physics) bound

@@ -105,6 +105,7 @@ SIGNATURES = {
     "gs_policy_values": (_i32, [C.POINTER(GsMlp), _vp, _i64, _vp, _vp]),
     "gs_rollout_collect": (_i32, [_vp, C.POINTER(GsMlp), C.POINTER(GsRollout), _vp, _u64, _u64, _i32, _vp]),
     "gs_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _f64, _vp, _vp, _vp]),
+    "gs_gae_zero_boot": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _f64, _vp, _vp, _vp]),
     "gs_mc_returns": (_i32, [_vp, _vp, _vp, _i32, _i64, _f64, _i32, _vp, _vp, _vp]),
     "gs_returns_to_full_episode": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "gs_valid_index_map": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),

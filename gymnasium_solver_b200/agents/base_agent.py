@@ -406,9 +406,7 @@ class BaseAgent(nn.Module):
         """One 64-byte record per sample (gs_rollout_pack: the bf16x3 layer-1 operand row + the sample's scalars) so the tensor-core
         update kernel copies a minibatch sample straight into its operand tile with one aligned access.  The 64x64 and 128x128
         networks have that kernel (observations of up to 7 features); the buffer is reused across rollouts."""
-        if tuple(getattr(self.config, "hidden_dims", ())) not in ((64, 64), (128, 128)) or "packed" in traj.tm:
-            return
-        if traj.tm["obs"].shape[-1] > 7:
+        if not self._tensor_path(traj.tm["obs"].shape[-1]) or "packed" in traj.tm:
             return
         total = traj.T * traj.n_envs
         buf = getattr(self, "_packed_records", None)
@@ -419,6 +417,18 @@ class BaseAgent(nn.Module):
             N.check(N.lib().gs_rollout_pack(C.byref(full.struct), N.ptr(buf), N.stream()))
         traj.tm["packed"] = buf
 
+    def _tensor_path(self, obs_dim: Optional[int] = None) -> bool:
+        """Does csrc/update_f16.cu serve this network (mirrors update_kernels.cu::tensor_path_for)?  Those kernels read per-minibatch
+        offset buffers and rollout records; everything else runs the FMA-pipe kernel."""
+        if tuple(getattr(self.config, "hidden_dims", ())) not in ((64, 64), (128, 128)):
+            return False
+        if os.environ.get("GS_UPDATE_IMPL", "tc") == "simt":
+            return False
+        if obs_dim is None:
+            shape = getattr(self.get_env("train").single_observation_space, "shape", None) or (1,)
+            obs_dim = int(shape[-1])
+        return obs_dim <= 7
+
     def _prepare_all(self, batches) -> None:
         """Sharded minibatches: run every gather pass of the rollout now and exchange ALL minibatch moments in ONE all-reduce
         (instead of one per minibatch on the critical path of every step)."""
@@ -427,7 +437,7 @@ class BaseAgent(nn.Module):
         if mom is None or mom.shape[0] != n:
             mom = self._mom_all = torch.zeros(n, 6, dtype=torch.float64, device=self.device)
         offs = None
-        if tuple(getattr(self.config, "hidden_dims", ())) == (64, 64):     # the tensor-core kernel reads translated offsets
+        if self._tensor_path():     # the tensor-core kernel reads translated offsets
             offs = getattr(self, "_offs_all", None)
             if offs is None or offs.shape != (n, B):
                 offs = self._offs_all = torch.empty(n, B, dtype=torch.int32, device=self.device)
@@ -443,7 +453,7 @@ class BaseAgent(nn.Module):
         key = _mix64(int(self.config.seed) ^ (self.current_epoch * 0x100000001B3))
         batches = [b for _, _, b in self.minibatches(traj, key)]
         fused = bool(batches) and self._fused_step_ok(batches[0])
-        tensor_path = tuple(getattr(self.config, "hidden_dims", ())) == (64, 64)
+        tensor_path = self._tensor_path()
         if fused and self.world_size > 1 and any(self._step_moments()):
             per_pass = max(1, len(batches) // max(1, int(self.n_epochs)))
             if tensor_path and per_pass >= 2 and len(batches) >= 2 * per_pass:

@@ -17,7 +17,10 @@ namespace gs {
 constexpr int kScanThreads = 64;
 constexpr int kUnroll = 8;
 
-template <bool HAS_BOOT>
+// BOOT: 0 = no bootstrap values (next value of a truncated step = the following step's value, as when the reference is given None),
+//       1 = dense (T, N) array, 2 = the array is identically ZERO and is not read (4 of the 22 B per element): what the collector
+//       holds under NEXT_STEP autoreset, where no final observation exists to bootstrap from
+template <int BOOT>
 __global__ void __launch_bounds__(kScanThreads)
 gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
            const uint8_t* __restrict__ timeouts, const float* __restrict__ last_values, const float* __restrict__ boot,
@@ -37,12 +40,12 @@ gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, 
             r[u] = ldg_stream(rewards + o);
             d[u] = ldg_stream(dones + o);
             to[u] = ldg_stream(timeouts + o);
-            bt[u] = HAS_BOOT ? ldg_stream(boot + o) : 0.0f;
+            bt[u] = BOOT == 1 ? ldg_stream(boot + o) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t o = (int64_t)(t - u) * N + n;
-            const float nv = (HAS_BOOT && to[u]) ? bt[u] : vnext;
+            const float nv = (BOOT != 0 && to[u]) ? bt[u] : vnext;
             const float nt = (d[u] && !to[u]) ? 0.0f : 1.0f;
             const float delta = fsub(fadd(r[u], fmul(fmul(gamma, nv), nt)), v[u]);
             g = fadd(delta, fmul(fmul(gl, g), nt));
@@ -55,7 +58,7 @@ gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, 
         const int64_t o = (int64_t)t * N + n;
         const float v = ldg_stream(values + o), r = ldg_stream(rewards + o);
         const uint8_t d = ldg_stream(dones + o), to = ldg_stream(timeouts + o);
-        const float nv = (HAS_BOOT && to) ? ldg_stream(boot + o) : vnext;
+        const float nv = (BOOT != 0 && to) ? (BOOT == 1 ? ldg_stream(boot + o) : 0.0f) : vnext;
         const float nt = (d && !to) ? 0.0f : 1.0f;
         const float delta = fsub(fadd(r, fmul(fmul(gamma, nv), nt)), v);
         g = fadd(delta, fmul(fmul(gl, g), nt));
@@ -276,8 +279,19 @@ int gs_gae(const float* values, const float* rewards, const uint8_t* dones, cons
     const unsigned blocks = (unsigned)((N + kScanThreads - 1) / kScanThreads);
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     cudaStream_t st = (cudaStream_t)stream;
-    if (bootstrapped) gae_kernel<true><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, bootstrapped, T, N, g, gl, adv, ret);
-    else gae_kernel<false><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, nullptr, T, N, g, gl, adv, ret);
+    if (bootstrapped) gae_kernel<1><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, bootstrapped, T, N, g, gl, adv, ret);
+    else gae_kernel<0><<<blocks, kScanThreads, 0, st>>>(values, rewards, dones, timeouts, last_values, nullptr, T, N, g, gl, adv, ret);
+    GS_LAUNCH_CHECK();
+    return 0;
+}
+
+int gs_gae_zero_boot(const float* values, const float* rewards, const uint8_t* dones, const uint8_t* timeouts, const float* last_values,
+                     int T, int64_t N, double gamma, double gae_lambda, float* adv, float* ret, void* stream) {
+    if (!values || !rewards || !dones || !timeouts || !last_values || !adv || !ret) GS_FAIL("gs_gae_zero_boot: NULL argument");
+    if (T <= 0 || N <= 0) GS_FAIL("gs_gae_zero_boot: empty rollout (T=%d, N=%lld)", T, (long long)N);
+    const unsigned blocks = (unsigned)((N + kScanThreads - 1) / kScanThreads);
+    const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
+    gae_kernel<2><<<blocks, kScanThreads, 0, (cudaStream_t)stream>>>(values, rewards, dones, timeouts, last_values, nullptr, T, N, g, gl, adv, ret);
     GS_LAUNCH_CHECK();
     return 0;
 }

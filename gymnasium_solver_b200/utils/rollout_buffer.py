@@ -55,12 +55,25 @@ class RolloutBuffer:
         self.dones_buf = z(dt=torch.uint8)
         self.logprobs_buf = z(dt=torch.float32)
         self.timeouts_buf = z(dt=torch.uint8)
-        self.bootstrapped_values_buf = z(dt=torch.float32)
+        # The reference's `bootstrapped_values_buf` (values of final observations at truncations).  The device vector envs autoreset on
+        # the NEXT step and emit no final observation, so nothing ever writes it: it is materialised (zeros) only when somebody
+        # asks for it, and until then the GAE scan runs its zero-bootstrap variant without reading 4 bytes per element.
+        self._bootstrapped_values_buf = None
         # episode accounting written by the collect kernel (RecordEpisodeStatistics values where done)
         self.ep_return_buf = z(dt=torch.float64)
         self.ep_length_buf = z(dt=torch.int32)
         self.pos = 0
         self.size = 0
+
+    @property
+    def bootstrapped_values_buf(self) -> torch.Tensor:
+        if self._bootstrapped_values_buf is None:
+            self._bootstrapped_values_buf = torch.zeros(self.maxsize, self.n_envs, dtype=torch.float32, device=self.device)
+        return self._bootstrapped_values_buf
+
+    @bootstrapped_values_buf.setter
+    def bootstrapped_values_buf(self, value) -> None:
+        self._bootstrapped_values_buf = value
 
     def begin_rollout(self, T: int) -> int:
         """Reserve T contiguous steps (wrapping to 0 when the tail is too short); returns the start index."""

@@ -303,9 +303,13 @@ class RolloutCollector:
         with torch.cuda.device(self.device):
             st = N.stream()
             if self.returns_type == "gae:rtg" and self.advantages_type == "gae":
-                N.check(L.gs_gae(N.ptr(b.values_buf[sl]), N.ptr(b.rewards_buf[sl]), N.ptr(b.dones_buf[sl]), N.ptr(b.timeouts_buf[sl]),
-                                 N.ptr(self._last_values), N.ptr(b.bootstrapped_values_buf[sl]), T, n, float(self.gamma),
-                                 float(self.gae_lambda), N.ptr(adv), N.ptr(ret), st))
+                if b._bootstrapped_values_buf is None:       # never materialised == identically zero: the scan does not read it
+                    N.check(L.gs_gae_zero_boot(N.ptr(b.values_buf[sl]), N.ptr(b.rewards_buf[sl]), N.ptr(b.dones_buf[sl]), N.ptr(b.timeouts_buf[sl]),
+                                               N.ptr(self._last_values), T, n, float(self.gamma), float(self.gae_lambda), N.ptr(adv), N.ptr(ret), st))
+                else:
+                    N.check(L.gs_gae(N.ptr(b.values_buf[sl]), N.ptr(b.rewards_buf[sl]), N.ptr(b.dones_buf[sl]), N.ptr(b.timeouts_buf[sl]),
+                                     N.ptr(self._last_values), N.ptr(b.bootstrapped_values_buf[sl]), T, n, float(self.gamma),
+                                     float(self.gae_lambda), N.ptr(adv), N.ptr(ret), st))
                 self._last_rollout_index_map = None
             elif self.returns_type in ("mc:episode", "mc:rtg"):
                 to = None if self.mc_treat_timeouts_as_terminals else b.timeouts_buf[sl]

@@ -236,6 +236,11 @@ int gs_gae(const float* values, const float* rewards, const uint8_t* dones, cons
            const float* last_values, const float* bootstrapped /* nullable (T,N) */, int T, int64_t N,
            double gamma, double gae_lambda /* Python floats of the reference, rounded to fp32 exactly as numpy does */,
            float* adv, float* ret, void* stream);
+/* The same with bootstrapped == an all-zero (T,N) array, WITHOUT reading one (18 instead of 22 bytes per element): the value the
+ * reference's collector holds whenever the vector env emits no final observation (NEXT_STEP autoreset: rollout_collector.py:262-284
+ * never fires), i.e. next value of a truncated step = 0.  Bit-identical to gs_gae given a zero array. */
+int gs_gae_zero_boot(const float* values, const float* rewards, const uint8_t* dones, const uint8_t* timeouts,
+                     const float* last_values, int T, int64_t N, double gamma, double gae_lambda, float* adv, float* ret, void* stream);
 /* compute_batched_mc_returns :67-91 (+ convert_returns_to_full_episode :93-113 when episode_mode).
  * timeouts nullable == all False (mc_treat_timeouts_as_terminals, rollout_collector.py:392-393).
  * last_terminal (nullable, (N,) int32): index of the last real terminal per env, -1 if none —

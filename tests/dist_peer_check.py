@@ -25,7 +25,7 @@ def stress(rank, world, dev):
 
     cfg = load_config("CartPole-v1", "ppo")
     cfg.n_envs, cfg.n_steps, cfg.batch_size, cfg.n_epochs = 128 * world, 32, 4096 * world, 1
-    cfg.model_id, cfg._hidden_dims = "mlp_small", resolve_model_spec("mlp_small").hidden_dims   # 128x128: gradients live in grads_flat
+    cfg.model_id, cfg._hidden_dims = "mlp_medium", resolve_model_spec("mlp_medium").hidden_dims   # 256x256 (FMA-pipe kernel): gradients live in grads_flat
     cfg.eval_freq_epochs, cfg.grad_allreduce = None, "peer"
     cfg.validate()
     agent = build_agent(cfg, rank=rank, world_size=world)
@@ -68,7 +68,7 @@ def training(rank, world, dev):
         cfg.validate()
         return build_agent(cfg, rank=rank, world_size=world)
 
-    for model_id in ("mlp_64x64", "mlp_small"):
+    for model_id in ("mlp_64x64", "mlp_small", "mlp_medium"):     # two-set / one-set tensor-core kernels, FMA-pipe kernel
         a, b = make("peer", model_id), make("nccl", model_id)
         assert a._peer is not None and a.grad_allreduce_mode == "peer" and b._peer is None and b.grad_allreduce_mode == "nccl"
         for it in range(4):

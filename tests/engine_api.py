@@ -24,13 +24,18 @@ def sync():
 
 # ---- returns ------------------------------------------------------------------------------------------------------
 def gae(values, rewards, dones, timeouts, last_values, boot, gamma, lam):
+    """boot: None (no bootstrap values), a (T, N) array, or the string "zero" (gs_gae_zero_boot: an all-zero array that is not read)."""
     v, r = cu(values, torch.float32), cu(rewards, torch.float32)
     d, to = cu(np.asarray(dones, dtype=np.uint8)), cu(np.asarray(timeouts, dtype=np.uint8))
     lv = cu(last_values, torch.float32)
-    b = None if boot is None else cu(boot, torch.float32)
     T, Nn = r.shape
     adv, ret = torch.empty_like(r), torch.empty_like(r)
-    N.check(N.lib().gs_gae(N.ptr(v), N.ptr(r), N.ptr(d), N.ptr(to), N.ptr(lv), N.ptr(b), T, Nn, gamma, lam, N.ptr(adv), N.ptr(ret), N.stream()))
+    if isinstance(boot, str):
+        assert boot == "zero"
+        N.check(N.lib().gs_gae_zero_boot(N.ptr(v), N.ptr(r), N.ptr(d), N.ptr(to), N.ptr(lv), T, Nn, gamma, lam, N.ptr(adv), N.ptr(ret), N.stream()))
+    else:
+        b = None if boot is None else cu(boot, torch.float32)
+        N.check(N.lib().gs_gae(N.ptr(v), N.ptr(r), N.ptr(d), N.ptr(to), N.ptr(lv), N.ptr(b), T, Nn, gamma, lam, N.ptr(adv), N.ptr(ret), N.stream()))
     sync()
     return adv.cpu().numpy(), ret.cpu().numpy()
 

@@ -50,6 +50,27 @@ def test_gae_vs_oracle_bit_exact(T, N):
         np.testing.assert_array_equal(ret, oret)
 
 
+@pytest.mark.parametrize("T,N", [(5, 3), (128, 1000), (33, 4097)])
+def test_gae_zero_bootstrap_variant_is_bit_identical_to_a_zero_array(T, N):
+    """gs_gae_zero_boot (what the collector calls: the bootstrap array of the reference is identically zero under NEXT_STEP
+    autoreset and is not read) == gs_gae given a dense zero array == the numpy oracle, bit for bit."""
+    import engine_api as E
+
+    rng = np.random.default_rng(T * 1000 + N)
+    v, r = rng.standard_normal((T, N)).astype(np.float32), rng.standard_normal((T, N)).astype(np.float32)
+    d = rng.random((T, N)) < 0.1
+    to = d & (rng.random((T, N)) < 0.4)
+    lv = rng.standard_normal(N).astype(np.float32)
+    zero = np.zeros((T, N), np.float32)
+    a0, r0 = E.gae(v, r, d, to, lv, zero, 0.99, 0.95)
+    a1, r1 = E.gae(v, r, d, to, lv, "zero", 0.99, 0.95)
+    oa, orr = R.gae(v, r, d, to, lv, zero, 0.99, 0.95)
+    np.testing.assert_array_equal(a1, a0)
+    np.testing.assert_array_equal(r1, r0)
+    np.testing.assert_array_equal(a1, oa)
+    np.testing.assert_array_equal(r1, orr)
+
+
 def test_gae_reference_known_answers():
     import engine_api as E
 
