@@ -476,6 +476,13 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     // programmatic dependent launch: the next minibatch's update kernel may be scheduled now; it runs its weight-independent
     // prologue and then blocks in griddepcontrol.wait until this grid has completed and flushed (parameters, moments, ticket)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 64 && ad.p) {                                   // bias corrections of THIS step, from the step count before it: two fp64 pow()
+        const int64_t step = *ad.step + 1;                      // calls that would otherwise sit in the serial phase of the last block
+        const double bc1 = 1.0 - pow((double)ad.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)ad.beta2, (double)step);
+        adam_c[0] = (float)((double)ad.lr / bc1);
+        adam_c[1] = (float)sqrt(bc2);
+    }
     // ---- phase A (every block): sum of the per-CTA partial vectors in a fixed order (16 contiguous groups of CTAs, then the
     //      groups in order); the result goes to grads (one rank) or straight into every rank's receive slot over NVLink
     //      (posted P2P stores, no reads cross the link)
@@ -515,14 +522,15 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     __threadfence();
     // ---- phase B (the last block to arrive) -----------------------------------------------------------------------------------
     if (peer.world > 1) {
-        __threadfence_system();
+        // st.release.sys is cumulative: the other blocks' slot stores (each fenced system-wide before its ticket, observed through the
+        // ticket + __threadfence above) are ordered before the flag -- no second system fence here
         if (tid < peer.world) st_release_sys(peer.flags[tid] + phase * peer.world + peer.rank, peer.epoch);
         if (tid < peer.world) {
             const uint32_t* fl = peer.flags[peer.rank] + phase * peer.world + tid;
             uint32_t spin = 0;
             while (ld_acquire_sys(fl) != peer.epoch) {
                 if (++spin > (1u << 28)) __trap();              // a rank left the lock-step call sequence: fail, do not hang
-                __nanosleep(64);
+                __nanosleep(32);
             }
         }
         __syncthreads();
@@ -550,14 +558,7 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
         const double t = block_sum(part[k], scratch);
         if (tid == 0) sq[k] = t;
     }
-    if (tid == 64 && ad.p) {
-        const int64_t step = *ad.step + 1;
-        const double bc1 = 1.0 - pow((double)ad.beta1, (double)step);
-        const double bc2 = 1.0 - pow((double)ad.beta2, (double)step);
-        adam_c[0] = (float)((double)ad.lr / bc1);
-        adam_c[1] = (float)sqrt(bc2);
-        *ad.step = step;
-    }
+    if (tid == 64 && ad.p) *ad.step = *ad.step + 1;           // adam_c was computed from the old count at kernel entry
     __syncthreads();
     const double total = sqrt(sq[0] + sq[1] + sq[2]);
     double coef = 1.0;
