@@ -153,6 +153,46 @@ def test_ppo_step_gather_modes_vs_oracle(D, hidden, A, mode, activation):
     assert m["opt/batch_count"] == len(src)
 
 
+def test_ppo_step_full_size_unfiltered_minibatch_is_closer_to_fp64_than_the_fp32_reference():
+    """The SAME 1M-sample minibatch WITHOUT moving samples off the kinks of the loss (ReLU zeros, ratio clip edges, clipped-value-loss
+    ties).  There the reference's own fp32 arithmetic is 6e-4 away from an fp64 evaluation of the same formulas (a handful of samples
+    falls on the other side of a kink), so agreement with torch fp32 to 1e-4 is not defined; what is: the engine (fp16x3 tensor-core
+    products, fp32 accumulation) must be at least as close to the fp64 evaluation as the fp32 reference is.  Reported, not just asserted."""
+    import engine_api as E
+    from gymnasium_solver_b200 import _native as N
+
+    T, Nn, D, A = 128, 65536, 4, 2
+    g = torch.Generator().manual_seed(0)
+    p = P.random_params(D, (64, 64), A, seed=1)
+    obs = torch.randn(T, Nn, D, generator=g) * 0.5
+    actions = torch.randint(0, A, (T, Nn), generator=g)
+    with torch.no_grad():
+        logits, v = P.forward(p, obs.reshape(-1, D))
+        lp_all = logits - logits.logsumexp(-1, keepdim=True)
+    old_logp = (lp_all.gather(-1, actions.reshape(-1, 1)).squeeze(-1) + 0.1 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    values_old = (v + 0.3 * torch.randn(T * Nn, generator=g)).reshape(T, Nn)
+    adv = torch.randn(T, Nn, generator=g)
+    ret = values_old + adv
+    B = 1 << 20
+    dev = [E.cu(obs), E.cu(actions.int()), E.cu(old_logp), E.cu(values_old), E.cu(adv), E.cu(ret)]
+    src = np.arange(3 * B, 4 * B)
+    batch, keep = E.make_batch(T, Nn, *dev, n=B, perm_offset=3 * B)
+    g_raw, _, m = E.update_step("ppo", E.dev_params(p), batch, _ppo_hp(N, track=False))
+    e, t = src // T, src % T
+    sel = lambda x: x[t, e]
+    kw = dict(clip_range=0.2, clip_range_vf=0.2, vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
+    _, flat64, _ = P.loss_and_grads(P.ppo_loss, {k: v_.double() for k, v_ in p.items()}, sel(obs).double(), sel(actions), sel(old_logp).double(),
+                                    sel(values_old).double(), sel(adv).double(), sel(ret).double(), **kw)
+    _, flat32, _ = P.loss_and_grads(P.ppo_loss, p, sel(obs), sel(actions), sel(old_logp), sel(values_old), sel(adv), sel(ret), **kw)
+    ref64, ref32 = flat64.numpy(), flat32.numpy()
+    rel = lambda a: float(np.linalg.norm(a - ref64) / np.linalg.norm(ref64))
+    e_engine, e_torch = rel(g_raw), rel(ref32)
+    print(f"unfiltered 1M-sample minibatch, L2 error vs fp64: engine {e_engine:.3e}, torch fp32 reference {e_torch:.3e}; "
+          f"engine max |err| / max |g| {np.abs(g_raw - ref64).max() / np.abs(ref64).max():.3e}")
+    assert e_engine <= max(e_torch, 1e-4) * 1.05
+    assert np.abs(g_raw - ref64).max() <= 5e-4 * np.abs(ref64).max()
+
+
 def test_ppo_step_full_size_minibatch_vs_oracle():
     """A C2-sized minibatch (1,048,576 samples gathered from a 128 x 65,536 rollout by the device permutation)."""
     import engine_api as E
@@ -191,8 +231,9 @@ def test_ppo_step_full_size_minibatch_vs_oracle():
     loss, flat, om = P.loss_and_grads(P.ppo_loss, p, sel(obs), sel(actions), sel(old_logp), sel(values_old), sel(adv), sel(ret),
                                       clip_range=0.2, clip_range_vf=0.2, vf_coef=0.5, ent_coef=0.01, normalize_adv=True)
     ref = flat.numpy()
-    # 1M-sample fp32 sums in a different order than torch's (the batch holds no sample on a ReLU / clipping kink)
-    _assert_grads_close(g_raw, ref, tol=2e-4)
+    # 1M-sample fp32 sums in a different order than torch's (the batch holds no sample on a ReLU / clipping kink): north_star's 1e-4,
+    # elementwise (of the gradient scale) and in L2
+    _assert_grads_close(g_raw, ref, tol=1e-4)
     assert np.linalg.norm(g_raw - ref) <= 1e-4 * np.linalg.norm(ref)
     np.testing.assert_allclose(m["opt/loss/total"], float(loss), rtol=1e-4)
     for k in PPO_METRICS:
