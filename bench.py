@@ -89,10 +89,26 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------- b200 arm
+OTHER_CONFIGS = {"c3": ("CartPole-v1", "reinforce_b200"), "c4_acrobot": ("Acrobot-v1", "ppo_b200"), "c4_mcar": ("MountainCar-v0", "ppo_b200")}
+OTHER_WORKLOADS = {"c3": "CartPole-v1:reinforce, policy_targets=returns + MC baseline, 262,144 envs total, n_steps=128, 64x64 MLP (BASELINE.json configs[2])",
+                   "c4_acrobot": "Acrobot-v1:ppo, 1,048,576 envs total sharded over the ranks, n_steps=128, 128x128 MLP (BASELINE.json configs[3])",
+                   "c4_mcar": "MountainCar-v0:ppo + StateCountBonus 50x50, 1,048,576 envs total sharded over the ranks, n_steps=128, 256x256 MLP (BASELINE.json configs[3])"}
+
+
 def build_agent_for_bench(args, rank, world):
     from gymnasium_solver_b200.agents import build_agent
     from gymnasium_solver_b200.utils.config import load_config
 
+    which = getattr(args, "config", "c2")
+    if which != "c2":
+        # BASELINE.json configs[2] / configs[3] exactly as their *_b200 YAML variants state them; the env count is the TOTAL over the
+        # ranks (strong scaling: "1M envs sharded across 1/2/4/8 B200"), so every rank owns n_envs / world envs and batch / world samples
+        env_id, variant = OTHER_CONFIGS[which]
+        cfg = load_config(env_id, variant)
+        cfg.eval_freq_epochs = None
+        cfg.max_env_steps = None
+        cfg.validate()
+        return build_agent(cfg, rank=rank, world_size=world), cfg
     cfg = load_config("CartPole-v1", "ppo_b200")
     cfg.n_envs = args.n_envs * world
     cfg.n_steps = args.n_steps
@@ -165,7 +181,8 @@ def run_b200(args):
     agent.pop_epoch_metrics()
 
     # ---- e2e: public API + per-step H2D of the hyper-parameter block and D2H of metrics / episode stats / weights ------
-    hp_host = torch.tensor([cfg.policy_lr, cfg.clip_range, cfg.clip_range_vf, cfg.vf_coef, cfg.ent_coef, 0, 0, 0],
+    num = lambda name: float(getattr(cfg, name, 0.0) or 0.0) if not isinstance(getattr(cfg, name, 0.0), dict) else 0.0
+    hp_host = torch.tensor([num("policy_lr"), num("clip_range"), num("clip_range_vf"), num("vf_coef"), num("ent_coef"), 0, 0, 0],
                            dtype=torch.float32).pin_memory()
     hp_dev = torch.zeros(8, dtype=torch.float32, device=dev)
     P = agent.policy_model.flat_params.numel()
@@ -193,12 +210,13 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (the fused update kernel), timed alone on its own stream ----------------------
     # (rank 0 only, with the collectives switched off: the microbench must not enter all-reduces the other ranks never join)
     roof = None
-    if rank == 0:
+    c2 = getattr(args, "config", "c2") == "c2"
+    if rank == 0 and c2:
         agent.world_size = 1
         roof = kernel_rooflines(agent, cfg, dev)
         agent.world_size = world
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and c2 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args, threads=1, budget_s=20.0)
 
     if rank == 0:
@@ -206,11 +224,12 @@ def run_b200(args):
         line = {
             "metric": "PPO env-steps/sec (collect+GAE+update)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/update), f64 (env physics)", "data": "synthetic",
-            "config": {"workload": "CartPole-v1:ppo, 65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP (BASELINE.json configs[1])",
-                       "n_envs_per_gpu": args.n_envs, "n_envs_total": args.n_envs * world, "n_steps": args.n_steps, "n_epochs": args.n_epochs,
-                       "batch_size_total": args.batch_size * world, "minibatches_per_step": (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs),
-                       "model_id": args.model_id, "parallelism": f"dp{world}: envs sharded; gradient mean per minibatch over NVLink peer memory inside gs_update_finish"
+            "scaling": "weak" if c2 else "strong", "vs_baseline": None, "dtype": "f32 (policy/update), f64 (env physics)", "data": "synthetic",
+            "config": {"workload": "CartPole-v1:ppo, 65,536 GPU-resident envs per GPU, n_steps=128, 64x64 MLP (BASELINE.json configs[1])" if c2
+                                   else OTHER_WORKLOADS[args.config],
+                       "n_envs_per_gpu": agent.local_n_envs, "n_envs_total": int(cfg.n_envs), "n_steps": int(cfg.n_steps), "n_epochs": int(agent.n_epochs),
+                       "batch_size_total": int(cfg.batch_size), "minibatches_per_step": (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs),
+                       "model_id": args.model_id if c2 else str(tuple(cfg.hidden_dims)), "parallelism": f"dp{world}: envs sharded; gradient mean per minibatch over NVLink peer memory inside gs_update_finish"
                                       if agent._peer is not None else f"dp{world}: envs sharded" + ("; NCCL grad all-reduce per minibatch" if world > 1 else ""),
                        "grad_allreduce": agent.grad_allreduce_mode,
                        "l2": "rollout working set (>=300 MB per GPU) exceeds the 126 MB L2; no explicit flush",
@@ -427,6 +446,8 @@ def parse_args(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4_acrobot", "c4_mcar"],
+                    help="c2 = BASELINE.json configs[1] (the metric's configuration, default); the others are configs[2] / configs[3] at full size, strong-scaled")
     ap.add_argument("--n-envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--n-steps", type=int, default=128)
     ap.add_argument("--batch-size", type=int, default=1048576, help="minibatch per GPU")
