@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgs_engine.so")
 
 ENV_KINDS = {"CartPole-v1": 0, "Acrobot-v1": 1, "MountainCar-v0": 2}
-WRAPPER_KINDS = {"MountainCarV0_StateCountBonus": 1, "CartPoleV1_RewardShaper": 2, "MountainCarV0_RewardShaper": 3}
+WRAPPER_KINDS = {"MountainCarV0_StateCountBonus": 1, "CartPoleV1_RewardShaper": 2, "MountainCarV0_RewardShaper": 3, "ScriptedReplay": 4}
 ACTIVATIONS = {"relu": 0, "tanh": 1}
 N_METRICS = 40
 

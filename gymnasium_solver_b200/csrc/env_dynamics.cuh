@@ -226,7 +226,22 @@ __device__ __forceinline__ void env_vec_step(EnvRegs& e, const EnvParams& P, int
                                              double& reward, bool& terminated, bool& truncated, double& ep_r, int& ep_l) {
     double r = 0.0;
     bool term = false, trunc = false;
-    if (e.needs_reset) {
+    if (KIND == GS_ENV_MOUNTAINCAR_V0 && P.wrapper == GS_WRAP_SCRIPTED_REPLAY) {
+        // table replay (see gs_engine.h): elapsed is the step index, the state holds the observation being shown
+        const float* tab = reinterpret_cast<const float*>(P.counts);
+        const int L = (int)P.wp[0];
+        if (e.needs_reset) { e.ep_ret = 0.0; e.ep_len = 0; }             // RecordEpisodeStatistics: the step after a done starts a new episode
+        const int k = e.elapsed < L - 1 ? e.elapsed : L - 1;
+        r = (double)tab[k];
+        term = tab[L + k] != 0.f;
+        trunc = tab[2 * L + k] != 0.f;
+        const int ko = e.elapsed + 1 < L ? e.elapsed + 1 : L;
+        e.s[0] = (double)tab[3 * L + 2 * ko];
+        e.s[1] = (double)tab[3 * L + 2 * ko + 1];
+        e.elapsed += 1;
+        e.ep_ret = dadd(e.ep_ret, r);
+        e.ep_len += 1;
+    } else if (e.needs_reset) {
         env_reset_state<KIND>(e.s, P.seed, (uint64_t)(P.gid0 + local), e.reset_count);
         e.reset_count += 1;
         e.elapsed = 0;

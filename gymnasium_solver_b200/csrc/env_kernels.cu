@@ -2,6 +2,8 @@
 // (reset / step as consumed at utils/rollout_collector.py:317 and :504), one thread per env.
 // HBM-bound: state is SoA fp64 ([S][N]) so every load / store of a warp is one contiguous line; the per-step
 // algorithmic traffic is the 98 / 106 / 58 B per env-step of SURVEY.md §8(d).
+#include <vector>
+
 #include "env_handle.cuh"
 
 namespace gs {
@@ -15,6 +17,11 @@ __global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(EnvDev h, float*
     EnvRegs e;
     e.reset_count = h.reset_count[i];
     env_reset_state<KIND>(e.s, h.params.seed, (uint64_t)(h.params.gid0 + i), e.reset_count);
+    if (KIND == GS_ENV_MOUNTAINCAR_V0 && h.params.wrapper == GS_WRAP_SCRIPTED_REPLAY) {   // scripted replay: reset shows obs[0] of the table
+        const float* tab = reinterpret_cast<const float*>(h.params.counts);
+        const int L = (int)h.params.wp[0];
+        e.s[0] = (double)tab[3 * L]; e.s[1] = (double)tab[3 * L + 1];
+    }
     e.reset_count += 1;
     e.elapsed = 0; e.ep_ret = 0.0; e.ep_len = 0; e.needs_reset = 0;
     env_store<KIND>(h, i, e);
@@ -129,11 +136,25 @@ int gs_wrapper_attach(gs_env_t* e, int wrapper_kind, const double* params_host, 
         case GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS: need = 5; kind = GS_ENV_MOUNTAINCAR_V0; break;
         case GS_WRAP_CARTPOLE_REWARD_SHAPER: need = 3; kind = GS_ENV_CARTPOLE_V1; break;
         case GS_WRAP_MOUNTAINCAR_REWARD_SHAPER: need = 3; kind = GS_ENV_MOUNTAINCAR_V0; break;
+        case GS_WRAP_SCRIPTED_REPLAY: {
+            kind = GS_ENV_MOUNTAINCAR_V0;
+            const int L = n_params > 0 ? (int)params_host[0] : 0;
+            if (L < 1 || L > 65536) GS_FAIL("gs_wrapper_attach: scripted replay needs 1..65536 steps, got %d", L);
+            need = 1 + 3 * L + 2 * (L + 1);
+            break;
+        }
         default: GS_FAIL("gs_wrapper_attach: unknown wrapper kind %d", wrapper_kind);
     }
     if (e->kind != kind) GS_FAIL("gs_wrapper_attach: wrapper %d does not apply to env kind %d", wrapper_kind, e->kind);
     if (n_params != need) GS_FAIL("gs_wrapper_attach: wrapper %d takes %d params, got %d", wrapper_kind, need, n_params);
     for (int i = 0; i < 5; ++i) e->params.wp[i] = i < n_params ? params_host[i] : 0.0;
+    if (wrapper_kind == GS_WRAP_SCRIPTED_REPLAY) {            // the tables live on the device as floats behind params.counts
+        std::vector<float> tab(n_params - 1);
+        for (int i = 1; i < n_params; ++i) tab[i - 1] = (float)params_host[i];
+        GS_CUDA(cudaSetDevice(e->device));
+        GS_CUDA(cudaMalloc((void**)&e->params.counts, sizeof(float) * tab.size()));
+        GS_CUDA(cudaMemcpy(e->params.counts, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
+    }
     if (wrapper_kind == GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS) {
         const double pb = params_host[0], vb = params_host[1];
         if (pb < 1 || vb < 1 || pb > 4096 || vb > 4096) GS_FAIL("gs_wrapper_attach: bins out of range");

@@ -44,3 +44,24 @@ def MountainCarV0_RewardShaper(env, position_reward_scale=100.0, velocity_reward
                        dict(id="MountainCarV0_RewardShaper", position_reward_scale=position_reward_scale,
                             velocity_reward_scale=velocity_reward_scale, height_reward_scale=height_reward_scale))
     return env
+
+
+def ScriptedReplay(env, rewards=(), terminated=(), truncated=None, observations=None):
+    """Engine-only test double (no reference counterpart in gym_wrappers/): a MountainCar-v0-shaped env (2 observations, 3 actions)
+    that ignores its actions and replays per-step tables -- the scripted fake envs of the reference's collector tests
+    (tests/test_rollouts_extra.py:161-240, tests/test_mc_baseline_mask.py, tests/test_rollouts.py:95-123) as a DEVICE env, so their
+    known answers are checked on the fused collect kernel.  Step k pays rewards[k] with terminated[k] / truncated[k] (k clamps at
+    the last entry) and shows observations[k+1]; reset shows observations[0].  No autoreset, no time limit."""
+    env = _require_device_env(env, "ScriptedReplay", "MountainCar-v0")
+    L = len(rewards)
+    if L < 1 or len(terminated) != L:
+        raise ValueError("ScriptedReplay: rewards and terminated must have the same non-zero length")
+    truncated = [False] * L if truncated is None else list(truncated)
+    observations = [[0.0, 0.0]] * (L + 1) if observations is None else [list(o) for o in observations]
+    if len(truncated) != L or len(observations) != L + 1 or any(len(o) != 2 for o in observations):
+        raise ValueError("ScriptedReplay: truncated needs L entries, observations L + 1 rows of 2")
+    params = [float(L)] + [float(r) for r in rewards] + [1.0 if t else 0.0 for t in terminated] + [1.0 if t else 0.0 for t in truncated]
+    for o in observations:
+        params += [float(o[0]), float(o[1])]
+    env.attach_wrapper("ScriptedReplay", params, dict(id="ScriptedReplay"))
+    return env

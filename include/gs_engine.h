@@ -38,6 +38,12 @@ extern "C" {
 #define GS_WRAP_MOUNTAINCAR_STATE_COUNT_BONUS 1 /* gym_wrappers/MountainCarV0/state_count_bonus.py:96-126 */
 #define GS_WRAP_CARTPOLE_REWARD_SHAPER        2 /* gym_wrappers/CartPoleV1/reward_shaper.py:43-77        */
 #define GS_WRAP_MOUNTAINCAR_REWARD_SHAPER     3 /* gym_wrappers/MountainCarV0/reward_shaper.py:60-102    */
+/* Scripted replay over MountainCar-v0's spaces (2 observations, 3 actions): the env ignores its actions and replays per-step tables --
+ * what the scripted fake envs of the reference's collector tests do (tests/test_rollouts_extra.py:161-240, test_mc_baseline_mask.py,
+ * test_rollouts.py:95-123), so their known answers run on the DEVICE collector.  params = {L, reward[L], terminated[L], truncated[L],
+ * obs[(L+1)*2]}: step k (0-based, k clamps at L-1) pays reward[k] with those flags and shows obs[k+1]; reset shows obs[0].  No
+ * autoreset and no time limit (the tables say when an episode ends); episode statistics restart after a done like everywhere else. */
+#define GS_WRAP_SCRIPTED_REPLAY               4
 
 /* ---- activations (utils/torch.py:15-25 ACTIVATION_MAPPING; engine supports these two) ------------ */
 #define GS_ACT_RELU 0
