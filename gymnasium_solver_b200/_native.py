@@ -89,6 +89,7 @@ SIGNATURES = {
     "gs_device_sm_count": (_i32, [_i32]),
     "gs_env_create": (_i32, [_i32, _i64, _i64, _u64, _i32, _i32, C.POINTER(_vp)]),
     "gs_env_destroy": (_i32, [_vp]),
+    "gs_env_set_obs_normalization": (_i32, [_vp, _vp, _vp, _i32]),
     "gs_env_obs_dim": (_i32, [_i32]),
     "gs_env_state_dim": (_i32, [_i32]),
     "gs_env_n_actions": (_i32, [_i32]),

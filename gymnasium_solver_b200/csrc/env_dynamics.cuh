@@ -27,6 +27,11 @@ struct EnvParams {
     uint32_t* counts;  // StateCountBonus tables [N][pb*vb]
     uint64_t seed;
     int64_t gid0;
+    // VecNormalizeStatic (gym_wrappers/vec_normalize_static.py:44-60): per observation dim 0 = pass through (non-finite bounds),
+    // 1 = (x - low) / den with den = (high - low) + 1e-8 in fp32, 2 = constant 0 (degenerate bounds)
+    int obs_norm;
+    int on_mode[6];
+    float on_low[6], on_den[6];
 };
 
 // registers of one env between vector steps
@@ -79,6 +84,18 @@ __device__ __forceinline__ void env_obs(const double s[4], float* o) {
         sincos(s[1], &s2, &c2);
         o[0] = (float)c1; o[1] = (float)s1; o[2] = (float)c2; o[3] = (float)s2;
         o[4] = (float)s[2]; o[5] = (float)s[3];
+    }
+}
+
+// fused VecNormalizeStatic: the observation every consumer sees (policy, rollout buffer, current-obs array) is the normalised one;
+// the per-env reward wrappers read the raw state, as in the reference where they sit below the vector wrapper
+template <int D>
+__device__ __forceinline__ void obs_normalize(const EnvParams& P, float* o) {
+    if (!P.obs_norm) return;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if (P.on_mode[d] == 1) o[d] = __fdiv_rn(__fsub_rn(o[d], P.on_low[d]), P.on_den[d]);
+        else if (P.on_mode[d] == 2) o[d] = 0.0f;
     }
 }
 
@@ -274,6 +291,7 @@ __device__ __forceinline__ void env_vec_step(EnvRegs& e, const EnvParams& P, int
     const bool done = term || trunc;
     e.needs_reset = done ? 1u : 0u;
     env_obs<KIND>(e.s, obs);
+    obs_normalize<EnvDims<KIND>::D>(P, obs);
     reward = r;
     terminated = term;
     truncated = trunc;

@@ -2,6 +2,7 @@
 // (reset / step as consumed at utils/rollout_collector.py:317 and :504), one thread per env.
 // HBM-bound: state is SoA fp64 ([S][N]) so every load / store of a warp is one contiguous line; the per-step
 // algorithmic traffic is the 98 / 106 / 58 B per env-step of SURVEY.md §8(d).
+#include <cmath>
 #include <vector>
 
 #include "env_handle.cuh"
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(EnvDev h, float*
     env_store<KIND>(h, i, e);
     float o[EnvDims<KIND>::D];
     env_obs<KIND>(e.s, o);
+    obs_normalize<EnvDims<KIND>::D>(h.params, o);
 #pragma unroll
     for (int d = 0; d < EnvDims<KIND>::D; ++d) obs[i * EnvDims<KIND>::D + d] = o[d];
 }
@@ -101,6 +103,8 @@ int gs_env_create(int kind, int64_t n_envs, int64_t env_id_offset, uint64_t seed
     e->params.max_steps = max_episode_steps > 0 ? max_episode_steps : (kind == GS_ENV_MOUNTAINCAR_V0 ? 200 : 500);
     e->params.wrapper = 0;
     e->params.counts = nullptr;
+    e->params.obs_norm = 0;
+    for (int d = 0; d < 6; ++d) { e->params.on_mode[d] = 0; e->params.on_low[d] = 0.f; e->params.on_den[d] = 1.f; }
     e->params.seed = seed;
     e->params.gid0 = env_id_offset;
     const size_t n = (size_t)n_envs;
@@ -165,6 +169,23 @@ int gs_wrapper_attach(gs_env_t* e, int wrapper_kind, const double* params_host, 
         GS_CUDA(cudaMemset(e->params.counts, 0, bytes));
     }
     e->params.wrapper = wrapper_kind;
+    return 0;
+}
+
+int gs_env_set_obs_normalization(gs_env_t* e, const float* low_host, const float* high_host, int n_dims) {
+    if (!e) GS_FAIL("gs_env_set_obs_normalization: NULL env");
+    const int D = gs_env_obs_dim(e->kind);
+    if (!low_host || !high_host) { e->params.obs_norm = 0; return 0; }          // NULL bounds: switch it off
+    if (n_dims != D) GS_FAIL("gs_env_set_obs_normalization: env has %d observation dims, got %d bounds", D, n_dims);
+    for (int d = 0; d < D; ++d) {
+        const float lo = low_host[d], hi = high_host[d];
+        const bool finite = std::isfinite(lo) && std::isfinite(hi);
+        e->params.on_mode[d] = (finite && hi > lo) ? 1 : ((finite && hi == lo) ? 2 : 0);
+        e->params.on_low[d] = lo;
+        const float scale = e->params.on_mode[d] == 1 ? hi - lo : 1.0f;         // vec_normalize_static.py:33: where(pos_scale, high - low, 1.0)
+        e->params.on_den[d] = (float)((double)scale + 1e-8);                    // float32 array + Python float -> float32
+    }
+    e->params.obs_norm = 1;
     return 0;
 }
 

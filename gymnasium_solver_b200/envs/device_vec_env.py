@@ -100,6 +100,24 @@ class DeviceVecEnv:
         except Exception:
             pass
 
+    def normalize_observations_static(self) -> None:
+        """VecNormalizeStatic of the reference (gym_wrappers/vec_normalize_static.py:20-60; ``normalize_obs: static``), fused into the
+        kernels that emit observations: bounded dims -> (x - low) / ((high - low) + 1e-8) in fp32, degenerate dims -> 0, unbounded
+        dims pass through.  The observation spaces are rewritten the way the wrapper rewrites them."""
+        sp = self.single_observation_space
+        low, high = sp.low.astype(np.float32), sp.high.astype(np.float32)
+        lo_c = (C.c_float * self.obs_dim)(*[float(x) for x in low])
+        hi_c = (C.c_float * self.obs_dim)(*[float(x) for x in high])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().gs_env_set_obs_normalization(self.handle, lo_c, hi_c, self.obs_dim))
+        finite = np.isfinite(low) & np.isfinite(high)
+        pos, zero = finite & (high > low), finite & (high == low)
+        low_n = np.where(pos | zero, 0.0, low).astype(np.float32)
+        high_n = np.where(pos, 1.0, np.where(zero, 0.0, high)).astype(np.float32)
+        self.single_observation_space = _Box((self.obs_dim,), low_n, high_n)
+        self.observation_space = _Box((self.num_envs, self.obs_dim), low_n, high_n)
+        self.normalize_obs = "static"
+
     def attach_wrapper(self, wrapper_id: str, params: list[float], spec: dict) -> None:
         arr = (C.c_double * len(params))(*[float(p) for p in params])
         with torch.cuda.device(self.device):

@@ -18,13 +18,20 @@ def build_env(env_id: str, *, n_envs: int = 1, seed: int = 0, max_episode_steps=
               env_id_offset: int = 0, **unused) -> DeviceVecEnv:
     if env_id not in DEVICE_ENV_IDS:
         raise KeyError(f"{env_id!r} is outside the b200 engine's scope; device envs: {DEVICE_ENV_IDS}")
-    for k in ("frame_stack", "frame_skip", "grayscale_obs", "resize_obs", "normalize_obs", "record_video"):
+    for k in ("frame_stack", "frame_skip", "grayscale_obs", "resize_obs", "record_video"):
         if unused.get(k):
             raise ValueError(f"{k} is not supported for device environments")
+    normalize_obs = unused.get("normalize_obs")
+    if normalize_obs in (True, "rolling"):            # gymnasium's NormalizeObservation (running statistics): not built
+        raise ValueError("normalize_obs='rolling' is not supported for device environments; use 'static' (VecNormalizeStatic)")
+    if normalize_obs not in (None, False, "static"):
+        raise ValueError(f"unknown normalize_obs: {normalize_obs!r}")
     env = DeviceVecEnv(env_id, int(n_envs), int(seed), max_episode_steps=max_episode_steps, device=device,
                        env_id_offset=env_id_offset, spec=env_spec)
     for spec in env_wrappers or ():
         env = EnvWrapperRegistry.apply(env, spec)
+    if normalize_obs == "static":                      # utils/environment.py:215-216: after the per-env wrappers and the episode statistics
+        env.normalize_observations_static()
     return env
 
 

@@ -195,6 +195,10 @@ int         gs_device_sm_count(int device);
 int gs_env_create(int env_kind, int64_t n_envs, int64_t env_id_offset /* global id of local env 0 */,
                   uint64_t seed, int max_episode_steps /* 0 -> 500/500/200 */, int device, gs_env_t** out);
 int gs_env_destroy(gs_env_t* env);
+/* VecNormalizeStatic (gym_wrappers/vec_normalize_static.py:20-60, applied by utils/environment.py:215-216 for normalize_obs="static"),
+ * fused into every kernel that emits observations: dims with finite low < high become (x - low) / ((high - low) + 1e-8) in fp32, finite
+ * degenerate dims 0, dims with non-finite bounds pass through.  low / high: HOST arrays of the env's Box bounds (NULL, NULL = off). */
+int gs_env_set_obs_normalization(gs_env_t* env, const float* low_host, const float* high_host, int n_dims);
 int gs_env_obs_dim(int env_kind);
 int gs_env_state_dim(int env_kind);
 int gs_env_n_actions(int env_kind);

@@ -244,3 +244,71 @@ def test_observation_space_bounds_and_recorder_protocol(golden_dir, env_id):
         assert e is env
     assert env.render_mode is None and env.unwrapped is env and not os.path.exists("unused.mp4")
     env.close()
+
+
+def _vec_normalize_static(obs, low, high):
+    """numpy restatement of VecNormalizeStatic._normalize_obs (gym_wrappers/vec_normalize_static.py:44-60), float32 like the wrapper."""
+    obs = obs.astype(np.float32, copy=False)
+    low, high = low.astype(np.float32), high.astype(np.float32)
+    finite = np.isfinite(low) & np.isfinite(high)
+    pos, zero = finite & (high > low), finite & (high == low)
+    scale = np.where(pos, (high - low).astype(np.float32), 1.0).astype(np.float32)
+    out = np.empty_like(obs, dtype=np.float32)
+    out[..., pos] = (obs[..., pos] - low[pos]) / (scale[pos] + 1e-8)
+    out[..., zero] = 0.0
+    out[..., ~(pos | zero)] = obs[..., ~(pos | zero)]
+    return out
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_static_observation_normalisation_is_fused_bit_exactly(env_id):
+    """normalize_obs="static" (utils/environment.py:215-216 -> VecNormalizeStatic): the device env with the fused normalisation shows,
+    bit for bit, what the wrapper computes from the raw env's observations -- at reset, through env.step and inside the fused collect
+    kernel -- and rewrites its observation space like the wrapper (bounded dims [0, 1], unbounded dims untouched)."""
+    import torch
+    from gymnasium_solver_b200.utils.environment import build_env
+    from gymnasium_solver_b200.utils.models import MLPActorCritic
+    from gymnasium_solver_b200.utils.rollout_collector import RolloutCollector
+
+    n, T = 300, 60
+    raw = build_env(env_id, n_envs=n, seed=5, max_episode_steps=25)
+    nrm = build_env(env_id, n_envs=n, seed=5, max_episode_steps=25, normalize_obs="static")
+    low, high = raw.single_observation_space.low, raw.single_observation_space.high
+    finite = np.isfinite(low) & np.isfinite(high)
+    np.testing.assert_array_equal(nrm.single_observation_space.low[finite], 0.0)
+    np.testing.assert_array_equal(nrm.single_observation_space.high[finite], 1.0)
+    np.testing.assert_array_equal(nrm.single_observation_space.high[~finite], high[~finite])
+    o_raw, _ = raw.reset()
+    o_nrm, _ = nrm.reset()
+    np.testing.assert_array_equal(o_nrm.cpu().numpy(), _vec_normalize_static(o_raw.cpu().numpy(), low, high))
+    rng = np.random.default_rng(1)
+    for t in range(T):
+        a = rng.integers(0, raw.n_actions, n)
+        o_raw, r0, te0, tr0, _ = raw.step(a)
+        o_nrm, r1, te1, tr1, _ = nrm.step(a)
+        np.testing.assert_array_equal(o_nrm.cpu().numpy(), _vec_normalize_static(o_raw.cpu().numpy(), low, high), err_msg=f"step {t}")
+        assert torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1)      # physics, rewards and flags are untouched
+    if finite.any():
+        got = o_nrm.cpu().numpy()[:, finite]
+        assert got.min() >= -1e-6 and got.max() <= 1 + 1e-6
+    # fused collect: the buffer holds normalised observations and the policy acted on them
+    env2 = build_env(env_id, n_envs=64, seed=9, max_episode_steps=25, normalize_obs="static")
+    ref2 = build_env(env_id, n_envs=64, seed=9, max_episode_steps=25)
+    model = MLPActorCritic(input_shape=(env2.obs_dim,), hidden_dims=(64, 64), output_shape=(env2.n_actions,), activation="relu").to(env2.device)
+    col = RolloutCollector(env2, model, 16, use_gae=True)
+    traj = col.collect()
+    obs_buf = traj.tm["obs"].cpu().numpy()
+    acts = traj.tm["actions"].cpu().numpy()
+    o, _ = ref2.reset()
+    for t in range(16):
+        np.testing.assert_array_equal(obs_buf[t], _vec_normalize_static(o.cpu().numpy(), low, high), err_msg=f"collect step {t}")
+        o, *_ = ref2.step(acts[t])
+
+
+def test_rolling_observation_normalisation_is_refused():
+    from gymnasium_solver_b200.utils.environment import build_env
+
+    with pytest.raises(ValueError, match="rolling"):
+        build_env("CartPole-v1", n_envs=4, seed=0, normalize_obs="rolling")
+    with pytest.raises(ValueError, match="rolling"):
+        build_env("CartPole-v1", n_envs=4, seed=0, normalize_obs=True)
