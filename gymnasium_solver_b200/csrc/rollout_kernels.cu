@@ -7,55 +7,9 @@
 // Collect is ONE launch per rollout: a CTA owns S environments for all T steps, env state lives in registers of the
 // S "env threads", all 256 threads of the CTA run the MLP tile GEMMs between env steps, and each step's
 // obs/action/logp/value/reward/done/timeout go straight into the time-major buffer as fully coalesced stores.
-#include "env_handle.cuh"
-#include "mlp_tile.cuh"
+#include "rollout_shared.cuh"
 
 namespace gs {
-
-struct RolloutDev {
-    int T, D;
-    int64_t N;
-    float *obs, *next_obs;
-    int32_t* actions;
-    float *logprobs, *values, *rewards;
-    uint8_t *dones, *timeouts;
-    float *last_obs, *last_values;
-    double* ep_return;
-    int32_t* ep_length;
-};
-
-// sample / mode + log-prob from the 4 head outputs of one row
-__device__ __forceinline__ void act_from_heads(const float (&out)[kNH], int A, int has_value, bool deterministic, float u,
-                                               int& action, float& logp, float& value) {
-    float lp[3] = {0.f, 0.f, 0.f};
-    log_softmax(out, A, lp);
-    int a = 0;
-    if (deterministic) {  // dist.mode: first maximum
-        float best = lp[0];
-#pragma unroll
-        for (int k = 1; k < 3; ++k)
-            if (k < A && lp[k] > best) { best = lp[k]; a = k; }
-    } else {              // inverse CDF: a = #{k : cdf_k <= u}, clamped
-        float cdf = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (k < A) { cdf += expf(lp[k]); a += (cdf <= u) ? 1 : 0; }
-        a = a < A - 1 ? a : A - 1;
-    }
-    action = a;
-    logp = a == 0 ? lp[0] : (a == 1 ? lp[1] : lp[2]);
-    value = has_value ? (A == 2 ? out[2] : out[3]) : 0.0f;
-}
-
-template <int D>
-__device__ __forceinline__ void store_obs_row(float* dst, int64_t row, const float* o) {
-    if (D == 4) reinterpret_cast<float4*>(dst)[row] = make_float4(o[0], o[1], o[2], o[3]);
-    else if (D == 2) reinterpret_cast<float2*>(dst)[row] = make_float2(o[0], o[1]);
-    else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) dst[row * D + d] = o[d];
-    }
-}
 
 __device__ __forceinline__ void write_xs_row(float* sm_xs, int row, const float* o, int D) {
     float x[kDP];
@@ -175,6 +129,12 @@ collect_kernel(EnvDev h, MlpDev m, RolloutDev buf, float* __restrict__ cur_obs, 
 }
 
 int validate_mlp(const gs_mlp_t* m);  // update_kernels.cu
+// collect_f16.cu: the same two entry points with the forward pass on the tensor cores (64x64 / 128x128 networks)
+bool f16_rollout_path(const gs_mlp_t* m);
+int launch_collect_f16(gs_env* env, const MlpDev& md, const RolloutDev& buf, float* cur_obs, uint64_t seed, uint64_t step0, int deterministic,
+                       cudaStream_t st);
+int launch_policy_act_f16(const MlpDev& md, const float* obs, int64_t n, uint64_t seed, uint64_t offset, int64_t row_offset, int deterministic,
+                          const float* uniforms, int32_t* actions, float* logp, float* value, float* logits, cudaStream_t st);
 
 static MlpDev mlp_dev(const gs_mlp_t* m) {
     MlpDev d;
@@ -205,6 +165,7 @@ static int dispatch_policy_act(const gs_mlp_t* m, const float* obs, int64_t n, u
                                cudaStream_t st) {
     if (validate_mlp(m)) return -1;
     if (!obs || n <= 0) GS_FAIL("policy_act: empty observation batch");
+    if (f16_rollout_path(m)) return launch_policy_act_f16(mlp_dev(m), obs, n, seed, offset, row_offset, deterministic, uniforms, actions, logp, value, logits, st);
     const int h1 = m->hidden1, h2 = m->hidden2;
 #define GS_PA(H1, H2, S) return launch_policy_act<TileCfg<H1, H2, S>>(m, obs, n, seed, offset, row_offset, deterministic, uniforms, actions, logp, value, logits, st)
     if (h1 == 64 && h2 == 64) GS_PA(64, 64, 64);
@@ -273,6 +234,7 @@ int gs_rollout_collect(gs_env_t* env, const gs_mlp_t* mlp, const gs_rollout_t* b
     d.logprobs = b->logprobs; d.values = b->values; d.rewards = b->rewards; d.dones = b->dones; d.timeouts = b->timeouts;
     d.last_obs = b->last_obs; d.last_values = b->last_values; d.ep_return = b->ep_return; d.ep_length = b->ep_length;
     cudaStream_t st = (cudaStream_t)stream;
+    if (f16_rollout_path(mlp)) return launch_collect_f16(env, mlp_dev(mlp), d, cur_obs, rng_seed, rng_offset, deterministic, st);
     switch (env->kind) {
         case GS_ENV_CARTPOLE_V1: return dispatch_collect<GS_ENV_CARTPOLE_V1>(env, mlp, d, cur_obs, rng_seed, rng_offset, deterministic, st);
         case GS_ENV_ACROBOT_V1: return dispatch_collect<GS_ENV_ACROBOT_V1>(env, mlp, d, cur_obs, rng_seed, rng_offset, deterministic, st);
