@@ -1,5 +1,9 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_update.py -x -q 2>&1 | tail -5
-GS_DEV_TRACK=0 python tests/dev_update_time.py --child 2>&1 | tail -1
-cp _exp/trace.so gymnasium_solver_b200/csrc/libgs_engine.so
-python tests/dev_f16_trace.py 2>&1 | tail -11
+for v in 0 1 2; do
+  cp _exp/cp$v.so gymnasium_solver_b200/csrc/libgs_engine.so
+  GS_DEV_TRACK=0 python tests/dev_update_time.py --child 2>&1 | tail -1
+done
+for v in 0 1 2; do
+  cp _exp/cp$v.so gymnasium_solver_b200/csrc/libgs_engine.so
+  GS_DEV_TRACK=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:update_f16 -s 6 -c 1 python tests/dev_update_time.py --child 2>&1 | grep -E "dram__bytes|gpu__time" | sed "s/^/variant $v: /"
+done
