@@ -1,9 +1,10 @@
 cd $GRAFT_REPO_ROOT
-for v in 0 1 2; do
-  cp _exp/cp$v.so gymnasium_solver_b200/csrc/libgs_engine.so
-  GS_DEV_TRACK=0 python tests/dev_update_time.py --child 2>&1 | tail -1
-done
-for v in 0 1 2; do
-  cp _exp/cp$v.so gymnasium_solver_b200/csrc/libgs_engine.so
-  GS_DEV_TRACK=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:update_f16 -s 6 -c 1 python tests/dev_update_time.py --child 2>&1 | grep -E "dram__bytes|gpu__time" | sed "s/^/variant $v: /"
-done
+mkdir -p gpurun_out
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_launch.log 2>&1
+python tests/dev_update_time.py --child > gpurun_out/r2_plain_update.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:update_f16 -s 6 -c 1 -o gpurun_out/r2_update_f16 -f python tests/dev_update_time.py --child > gpurun_out/r2_ncu_update.log 2>&1
+GS_DEV_ITERS=1 python tests/dev_step_profile.py > gpurun_out/r2_plain_step.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"collect_f16|gae_kernel|update_finish|gather_offsets|rollout_pack" -s 40 -c 8 -o gpurun_out/r2_step_kernels -f python tests/dev_step_profile.py > gpurun_out/r2_ncu_step.log 2>&1
+tail -2 gpurun_out/r2_ncu_launch.log gpurun_out/r2_ncu_update.log gpurun_out/r2_ncu_step.log
+ls -la gpurun_out/*.ncu-rep gpurun_out/r2_launches.csv
