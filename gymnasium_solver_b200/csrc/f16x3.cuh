@@ -80,8 +80,7 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c, int rows) {
 //                2: [b2_hi b2_lo at 14, 15]                                      x16 . ws2 = b2
 //                3: [Wh_hi(r) at r | Wh_hi(r) at 4+r | Wh_lo(r) at 8+r]          head rows r < 4 (policy logits, then the value row)
 template <int H>
-__device__ __forceinline__ void stage_weights(const MlpDev& m, unsigned char* w2hi, unsigned char* w2lo, unsigned char* ws, int tid, int n_threads) {
-    const int D = m.D, A = m.A;
+__device__ __forceinline__ void stage_w2(const MlpDev& m, unsigned char* w2hi, unsigned char* w2lo, int tid, int n_threads) {
 #pragma unroll 4
     for (int i = tid; i < H * H / 4; i += n_threads) {      // independent 16-byte loads, several in flight per thread
         const int j = i / (H / 4), k = 4 * (i % (H / 4));
@@ -93,6 +92,10 @@ __device__ __forceinline__ void stage_weights(const MlpDev& m, unsigned char* w2
         *reinterpret_cast<uint2*>(w2hi + o) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(w2lo + o) = make_uint2(l0, l1);
     }
+}
+template <int H>
+__device__ __forceinline__ void stage_ws(const MlpDev& m, unsigned char* ws, int tid) {
+    const int D = m.D, A = m.A;
     if (tid < H) {                                            // WS row j: every load of the row is independent -> one round trip
         const int j = tid;
         float w[kMaxD], whv[4];
@@ -121,6 +124,11 @@ __device__ __forceinline__ void stage_weights(const MlpDev& m, unsigned char* w2
             *reinterpret_cast<uint4*>(ws + j * 128 + ((c ^ (j & 7)) << 4)) =
                 make_uint4(e[8 * c] | (e[8 * c + 1] << 16), e[8 * c + 2] | (e[8 * c + 3] << 16), e[8 * c + 4] | (e[8 * c + 5] << 16), e[8 * c + 6] | (e[8 * c + 7] << 16));
     }
+}
+template <int H>
+__device__ __forceinline__ void stage_weights(const MlpDev& m, unsigned char* w2hi, unsigned char* w2lo, unsigned char* ws, int tid, int n_threads) {
+    stage_w2<H>(m, w2hi, w2lo, tid, n_threads);
+    stage_ws<H>(m, ws, tid);
 }
 
 }  // namespace hfu

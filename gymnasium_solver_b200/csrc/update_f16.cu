@@ -672,7 +672,7 @@ update_f16_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ adv
 }
 
 // ---- host launchers (called from update_kernels.cu) -----------------------------------------------------------------------------
-int f16_sets(int H) { return H == 64 ? 2 : 1; }
+int f16_sets(int H) { return H == 64 ? 2 : 1; }   // partial gradient vectors per CTA (update_wide.cu's 256-wide kernels: 1)
 
 template <int H, int ALGO>
 static int launch_f16_h(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,

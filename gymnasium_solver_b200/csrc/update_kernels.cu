@@ -728,6 +728,7 @@ struct UpdateWs {  // workspace carve-up
 };
 
 static int update_grid(int device) { return 2 * sm_count(device); }
+int64_t wide_scratch_bytes(int64_t max_batch);   // update_wide.cu
 
 static int64_t ws_bytes(const gs_mlp_t* m, int device, int64_t max_batch) {
     const int64_t P = mlp_param_count(m->obs_dim, m->hidden1, m->hidden2, m->n_actions, m->has_value);
@@ -738,6 +739,7 @@ static int64_t ws_bytes(const gs_mlp_t* m, int device, int64_t max_batch) {
     b += ((int64_t)(m->hidden1 + m->hidden2) * 4 + 255) / 256 * 256;
     b += 256;
     b += (max_batch * 4 + 255) / 256 * 256;
+    if (m->hidden1 == 256 && m->hidden2 == 256) b += wide_scratch_bytes(max_batch);   // staged W2 + the h1 / dz2 tiles of update_wide.cu
     return b;
 }
 
@@ -759,13 +761,19 @@ int launch_update_f16(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool
                      const uint32_t* offs, const void* records, float* grad_partials, int64_t pstride, double* metric_partials, uint32_t* dead,
                      int grid, cudaStream_t st);
 int f16_sets(int H);
+// 256 x 256 relu networks: update_wide.cu (fused kernel + layer-2 weight-gradient kernel over tiles stored in the workspace)
+template <int ALGO>
+int launch_update_wide(const MlpDev& md, const BatchDev& b, const HpDev& hp, bool track, const double* adv_mom, const double* ret_mom,
+                       const uint32_t* offs, const void* records, void* scratch, float* grad_partials, int64_t pstride, double* metric_partials,
+                       uint32_t* dead, int grid, cudaStream_t st);
 int launch_rollout_pack(const BatchDev& b, void* packed, int device, cudaStream_t st);
 int launch_batch_pack(const BatchDev& b, const uint32_t* offs, void* packed, cudaStream_t st);
 
 // does the tensor-core kernel serve this network / rollout?  (everything else runs update_kernel on the fp32 FMA pipe)
 static int update_impl();
-static bool tensor_path_for(int h1, int h2, int obs_dim, int64_t T, int64_t N) {
-    return h1 == h2 && (h1 == 64 || h1 == 128) && obs_dim <= 7 && update_impl() == 0 && T * N < (1ll << 32);
+static bool tensor_path_for(int h1, int h2, int act, int obs_dim, int64_t T, int64_t N) {
+    const bool width = h1 == 64 || h1 == 128 || (h1 == 256 && act == GS_ACT_RELU);
+    return h1 == h2 && width && obs_dim <= 7 && update_impl() == 0 && T * N < (1ll << 32);
 }
 
 // Sample-id translation of the whole minibatch in one pass: offs[pos] = time-major offset of minibatch position pos.  The
@@ -793,7 +801,7 @@ __global__ void gather_offsets_kernel(BatchDev b, uint32_t* __restrict__ offs, c
     }
 }
 
-// 0 = tensor cores where a kernel exists (64x64, 128x128), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
+// 0 = tensor cores where a kernel exists (64x64, 128x128, 256x256 relu), 1 = fp32 SIMT everywhere.  GS_UPDATE_IMPL=simt|tc overrides at load.
 static int g_update_impl = -1;
 static int update_impl() {
     if (g_update_impl < 0) {
@@ -823,7 +831,7 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     if (track || mf0 || mf1 || b.defer_reduce) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead) + 64, st));
     if (mf0) adv_mom = w.sq;
     if (mf1) ret_mom = w.sq + 3;
-    const bool tensor_path = tensor_path_for(C::H1, C::H2, md.D, b.T, b.N);
+    const bool tensor_path = tensor_path_for(C::H1, C::H2, md.act, md.D, b.T, b.N);
     if (!C::kPersist && !tensor_path) GS_CUDA(cudaMemsetAsync(grads_flat, 0, (size_t)P * 4, st));
     if (!tensor_path && (mf0 || mf1)) {
         int64_t blocks = (b.n + 255) / 256;
@@ -852,7 +860,13 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
             records = scratch;
             koffs = nullptr;
         }
-        const int rc = launch_update_f16<ALGO>(md, b, hp, track, adv_mom, ret_mom, koffs, records, w.grad_partials, pstride, w.metric_partials, w.dead, ctas, st);
+        int rc;
+        if (C::H1 == 256) {   // staged W2 + stored tiles live behind this minibatch's offsets (ws_bytes(b.n) covers them)
+            void* wide = (char*)w.offs + (b.n * 4 + 255) / 256 * 256;
+            rc = launch_update_wide<ALGO>(md, b, hp, track, adv_mom, ret_mom, koffs, records, wide, w.grad_partials, pstride, w.metric_partials, w.dead, ctas, st);
+        } else {
+            rc = launch_update_f16<ALGO>(md, b, hp, track, adv_mom, ret_mom, koffs, records, w.grad_partials, pstride, w.metric_partials, w.dead, ctas, st);
+        }
         if (scratch) GS_CUDA(cudaFreeAsync(scratch, st));
         if (rc) return -1;
     } else {
@@ -966,7 +980,7 @@ int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv,
     GS_CUDA(cudaMemsetAsync(moments, 0, 6 * sizeof(double), st));
     const float* f0 = want_adv ? b.adv : nullptr;
     const float* f1 = want_ret ? b.ret : nullptr;
-    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->obs_dim, b.T, b.N);
+    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->activation, mlp->obs_dim, b.T, b.N);
     if (tensor_path) {
         const UpdateWs w = carve(workspace, mlp, update_grid(device));
         gather_offsets_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b, b.offsets ? b.offsets : w.offs, f0, f1, moments);
@@ -1111,7 +1125,7 @@ int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_fini
     const int grid_max = update_grid(device);
     int n_cta = (int)(n_tiles < grid_max ? n_tiles : grid_max);
     int n_metric_cta = n_cta;
-    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->obs_dim, batch->T, batch->N);
+    const bool tensor_path = tensor_path_for(mlp->hidden1, mlp->hidden2, mlp->activation, mlp->obs_dim, batch->T, batch->N);
     if (tensor_path) {
         const int sms = sm_count(device);
         n_tiles = (batch->n + 127) / 128;

@@ -20,7 +20,8 @@ import engine_api as E
 from oracle import policy as P
 T, Nn, D, A = 128, 65536, 4, 2
 g = torch.Generator().manual_seed(0)
-p = P.random_params(D, (64, 64), A, seed=1)
+HID = int(os.environ.get("GS_DEV_HIDDEN", "64"))
+p = P.random_params(D, (HID, HID), A, seed=1)
 obs = torch.randn(T, Nn, D, generator=g) * 0.5
 actions = torch.randint(0, A, (T, Nn), generator=g)
 z = torch.randn(T, Nn, generator=g)
@@ -31,7 +32,8 @@ if not os.environ.get("GS_DEV_UNPACKED"):
     E.pack_rollout(batch, keep)      # as the agent does once per rollout: the kernel gathers 64-byte records
 hp_track = int(os.environ.get("GS_DEV_TRACK", "1"))
 hp = N.GsPpoHparams(); hp.clip_range, hp.clip_range_vf, hp.vf_coef, hp.ent_coef, hp.normalize_adv, hp.track_activations = 0.2, 0.2, 0.5, 0.01, 1, hp_track
-m = N.mlp_struct_from_params(E.dev_params(p), "relu")
+pd = E.dev_params(p)      # keep the device tensors alive: the struct holds raw pointers
+m = N.mlp_struct_from_params(pd, "relu")
 Pn = N.lib().gs_mlp_param_count(C.byref(m))
 wsb = N.lib().gs_update_workspace_bytes(C.byref(m), 0, n)
 ws = torch.empty(wsb, dtype=torch.uint8, device="cuda"); grads = torch.empty(Pn, device="cuda"); met = torch.zeros(N.N_METRICS, dtype=torch.float64, device="cuda")
@@ -46,7 +48,7 @@ e0.record()
 for _ in range(K): step()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(f"{os.path.basename(lib or 'default')}: gs_ppo_step {ms*1000:.1f} us / 1M-sample minibatch  ({2 * n * 13632 / ms / 1e9:.1f} TFLOP/s algorithmic)  |grad| {float(grads.norm()):.6e}")
+print(f"{os.path.basename(lib or 'default')}: gs_ppo_step {ms*1000:.1f} us / 1M-sample minibatch  ({6 * n * (D * HID + HID * HID + (A + 1) * HID) / ms / 1e9:.1f} TFLOP/s algorithmic)  |grad| {float(grads.norm()):.6e}")
 if os.environ.get("GS_DEV_PROFILE"):
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
