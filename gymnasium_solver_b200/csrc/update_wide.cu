@@ -80,10 +80,37 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 }  // namespace wfu
 
-// W2 -> operand layout in the workspace (hi then lo), once per step
+// W2 (rows j, columns k: dgrad's B) and W2^T (rows k, columns j: the forward pass's B) -> operand layout in the workspace, each as
+// hi then lo, once per step.  Both are read MN-major (K = row), so one 16 KB ring stage = 32 rows of all four 64-column slabs.
 __global__ void stage_w2_kernel(MlpDev m, unsigned char* __restrict__ staged) {
-    hfu::stage_w2<wfu::H>(m, staged, staged + wfu::kW2Prec, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
+    using namespace wfu;
+    const int n_threads = (int)(gridDim.x * blockDim.x);
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < H * H / 4; i += n_threads) {
+        const int j = i / (H / 4), k = 4 * (i % (H / 4));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(m.w2 + j * H) + (i % (H / 4)));
+        uint32_t h0, l0, h1, l1;
+        hfu::split_pair(w.x, w.y, h0, l0);
+        hfu::split_pair(w.z, w.w, h1, l1);
+        const uint32_t o = hfu::tile_off(j, k, H);
+        *reinterpret_cast<uint2*>(staged + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(staged + kW2Prec + o) = make_uint2(l0, l1);
+        const uint32_t hv[4] = {h0 & 0xFFFFu, h0 >> 16, h1 & 0xFFFFu, h1 >> 16}, lv[4] = {l0 & 0xFFFFu, l0 >> 16, l1 & 0xFFFFu, l1 >> 16};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {                          // transposed copy: element (k + e, j)
+            const uint32_t ot = hfu::tile_off(k + e, j, H);
+            *reinterpret_cast<unsigned short*>(staged + 2 * kW2Prec + ot) = (unsigned short)hv[e];
+            *reinterpret_cast<unsigned short*>(staged + 3 * kW2Prec + ot) = (unsigned short)lv[e];
+        }
+    }
 }
+
+// Development aid (GS_NVCC_EXTRA=-DGS_WIDE_TRACE): clock64() stamps of one tile of CTA 7 -- compute warp 0 (role 0) and the MMA warp (role 1)
+#ifdef GS_WIDE_TRACE
+__device__ long long g_wide_trace[2][24];
+#define GS_WT(role, k) do { if (blockIdx.x == 7 && i == 5 && lane == 0 && (role == 1 || warp == 0)) g_wide_trace[role][k] = clock64(); } while (0)
+#else
+#define GS_WT(role, k) do { } while (0)
+#endif
 
 template <int ALGO, bool TRACK>
 __global__ void __launch_bounds__(wfu::kWideThreads, 1)
@@ -136,8 +163,10 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
     const int n_my = (int)((n_tiles - blockIdx.x + G - 1) / G);                   // tiles of this CTA (>= 1)
     const uint32_t sBase = smem_u32(sm);
     const uint32_t sPhi = sBase + oPhi, sPlo = sBase + oPlo, sX = sBase + oX, sWS = sBase + oWS, sRing = sBase + oRing;
+    const int rot = (int)(blockIdx.x & 15u);                                      // block order rotation of this CTA (loader and MMA warp agree)
 
     // ============================================ loader warp: W2 blocks -> ring ===============================================
+    // stage = K rows 32 blk .. 32 blk + 31 of one precision of W2^T (forward: rows k) or W2 (dgrad: rows j), all four 64-column slabs
     if (warp_u == (uint32_t)kCW + 1u) {
         if (lane == 0) {
             uint32_t q = 0;
@@ -147,154 +176,166 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
                 for (int s = 0; s < kStagesPerTile; ++s, ++q) {
                     const uint32_t slot = q % kRing, round = q / kRing;
                     mbar_wait(&bars[BAR_EMPTY + slot], (round & 1u) ^ 1u);
+#ifdef GS_WIDE_NOLOAD   // timing experiment: the ring is only filled for the first tile (results are wrong)
+                    if (i > 0) { mbar_arrive(&bars[BAR_FULL + slot]); continue; }
+#endif
                     mbar_expect_tx(&bars[BAR_FULL + slot], kStage);
-                    const int s16 = s & 15;
-                    const uint32_t prec = s16 < 8 ? 1u : 0u;                       // the lo blocks first (small terms first)
-                    const uint32_t blk = (uint32_t)(s16 & 7) >> 1, half = (uint32_t)s16 & 1u;
-                    const unsigned char* src = w2s + prec * kW2Prec;
+                    const int s16 = (s + rot) & 15;                               // CTAs walk the 16 blocks of a phase from different starts
+                    const uint32_t prec = s16 < 8 ? 1u : 0u, blk = (uint32_t)s16 & 7u;
+                    const unsigned char* src = w2s + (s < 16 ? 2u * kW2Prec : 0u) + prec * kW2Prec + blk * 4096u;
                     const uint32_t dst = sRing + slot * kStage;
-                    if (s < 16) {                                                 // forward: k-slab `blk`, j rows 128 half ..
-                        bulk_g2s(dst, src + blk * (H * 128u) + half * 16384u, kStage, &bars[BAR_FULL + slot]);
-                    } else {                                                      // dgrad: j rows 64 blk .., k slabs 2 half, 2 half + 1
-                        bulk_g2s(dst, src + (2u * half) * (H * 128u) + blk * 8192u, 8192u, &bars[BAR_FULL + slot]);
-                        bulk_g2s(dst + 8192u, src + (2u * half + 1u) * (H * 128u) + blk * 8192u, 8192u, &bars[BAR_FULL + slot]);
-                    }
+#pragma unroll
+                    for (uint32_t sl = 0; sl < 4u; ++sl) bulk_g2s(dst + sl * 4096u, src + sl * (H * 128u), 4096u, &bars[BAR_FULL + slot]);
                 }
             }
         }
         return;
     }
 
-    // ============================================ MMA-issuing warp (one thread) ================================================
+    // ============================================ MMA-issuing warp ==============================================================
+    // Warp-uniform control flow; every MMA group is issued by the elected lane under elect.sync (one UTCHMMA per instruction instead of the
+    // per-instruction election loop a thread-dependent branch compiles to).  The bulk stores of the tiles are lane 0's (bulk groups are
+    // per thread).  The tensor pipe executes a CTA's MMAs in issue order, so a commit also stands for the groups issued before it.
     if (warp_u == (uint32_t)kCW) {
-        if (lane == 0) {
-            const uint32_t T = tmem;
-            uint32_t q = 0;                                                       // ring stage counter (same sequence as the loader's)
-            auto kfeat = [](int kk) -> uint32_t { return (uint32_t)(kk >> 2) * kSlab + (uint32_t)(kk & 3) * 32u; };
-            auto issue_l1 = [&](int i) {
-                const uint32_t sXg = sX + 32u * (1u + ((uint32_t)i & 1u));
-                mma_f16(T + cAcc, desc(sXg), desc(sWS + 32u), idesc_f16(128, H, 0, 0), 0u);
-                mma_f16(T + cAcc, desc(sXg), desc(sWS), idesc_f16(128, H, 0, 0), 1u);
+        const uint32_t T = tmem;
+        uint32_t q = 0;                                                           // ring stage counter (same sequence as the loader's)
+        // descriptors: the start-address field counts 16-byte units, so operands are stepped by adding (bytes >> 4)
+        const uint64_t dPhi = desc(sPhi), dPlo = desc(sPlo);                      // K-major A (rows = samples)
+        const uint64_t dPhiT = desc(sPhi, kSlab), dPloT = desc(sPlo, kSlab);      // MN-major A (M = features: LBO = slab stride)
+        const uint64_t dG = desc(sX, kSlab);                                      // g16 group as MN-major B of W-c / W-d
+        const uint64_t dWS = desc(sWS), dWSh = desc(sWS + 96u, H * 128u);         // WS groups; head rows as MN-major B
+        constexpr uint32_t idFull = idesc_f16(128, H, 0, 0), idFullT = idesc_f16(128, H, 0, 1);
+        constexpr uint32_t idHeads = idesc_f16(128, 16, 0, 1), idW = idesc_f16(128, 16, 1, 1);
+        auto kfeat = [](int kk) -> uint64_t { return (uint64_t)(((uint32_t)(kk >> 2) * kSlab + (uint32_t)(kk & 3) * 32u) >> 4); };
+        auto issue_l1 = [&](int i) {
+            const uint64_t dXg = desc(sX + 32u * (1u + ((uint32_t)i & 1u)));
+            if (elect_one()) {
+                mma_f16(T + cAcc, dXg, dWS + 2u, idFull, 0u);                     // x_hi . W1_lo first (small terms first)
+                mma_f16(T + cAcc, dXg, dWS, idFull, 1u);
                 mma_commit(&bars[BAR_Z1]);
-            };
-            auto store_tile = [&](int64_t tile, uint32_t which) {                 // P (hi, lo) -> scratch slot `which` (0: h1, 1: dz2)
+            }
+            __syncwarp();
+        };
+        auto store_tile = [&](int64_t tile, uint32_t which) {                     // P (hi, lo) -> scratch slot `which` (0: h1, 1: dz2)
+#ifndef GS_WIDE_NOSTORE
+            if (lane == 0) {
                 unsigned char* dst = tiles + (size_t)tile * kTileBytes + (size_t)which * 2u * kTile;
 #pragma unroll 1
                 for (uint32_t c = 0; c < 2u * kTile; c += 16384u) bulk_s2g(dst + c, sPhi + c, 16384u);   // P_lo directly follows P_hi
                 bulk_commit();
-            };
-            mbar_wait(&bars[RDY_X], 0); fence_after_sync();
-            issue_l1(0);
+            }
+            __syncwarp();
+#endif
+        };
+        // 32 small MMAs of a 16-column weight-gradient accumulator: acc[mb] (+)= A^T(P) . B, both MN-major, K = the tile's 128 samples
+        auto issue_wgrad16 = [&](uint32_t col, uint64_t dB, uint32_t acc_w) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint64_t a0 = (pass == 0 ? dPloT : dPhiT) + (uint64_t)((uint32_t)mb * 2u * kSlab >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) mma_f16(T + col + 16u * mb, a0 + (uint64_t)(kk * 128), dB + (uint64_t)(kk * 128), idW, (pass | kk) ? 1u : acc_w);
+                }
+        };
+        // one GEMM phase: acc (+)= P . B over the 16 ring stages (B MN-major, N = 256, two k-steps per stage); `first_acc` = accumulate flag of
+        // the phase's first MMA; the last stage also commits `done`
+        auto gemm_phase = [&](uint32_t first_acc, uint64_t* done) {
 #pragma unroll 1
-            for (int i = 0; i < n_my; ++i) {
-                const uint32_t p = (uint32_t)i & 1u;
-                const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * G;
-                const uint32_t sXg = sX + 32u * (1u + p);
-                const uint32_t acc_w = (i % kFlushTiles) != 0 ? 1u : 0u;
-                // ---- forward: z2 = b2 + h1 . W2^T ----
-                mbar_wait(&bars[RDY_H1], p); fence_after_sync();
-                store_tile(tile, 0u);
-                mma_f16(T + cAcc, desc(sXg), desc(sWS + 64u), idesc_f16(128, H, 0, 0), 0u);
-#pragma unroll 1
-                for (int s = 0; s < 16; ++s, ++q) {
-                    const uint32_t slot = q % kRing, round = q / kRing;
-                    const bool lo = s < 8;
-                    const uint32_t blk = (uint32_t)(s & 7) >> 1, half = (uint32_t)s & 1u;
-                    const uint32_t sB = sRing + slot * kStage;
-                    mbar_wait(&bars[BAR_FULL + slot], round & 1u);
-                    fence_after_sync();
+            for (int s = 0; s < 16; ++s, ++q) {
+                const uint32_t slot = q % kRing, round = q / kRing;
+                const int sr = (s + rot) & 15;
+                const bool lo = sr < 8;
+                const uint32_t blk = (uint32_t)sr & 7u;                           // K index 32 blk ..: slab blk / 2 of P, byte 64 (blk & 1) of its rows
+                const uint64_t dB = desc(sRing + slot * kStage, 4096u);
+                const uint64_t aoff = (uint64_t)(((blk >> 1) * kSlab + (blk & 1u) * 64u) >> 4);
+                const uint32_t later = s ? 1u : first_acc;
+                mbar_wait(&bars[BAR_FULL + slot], round & 1u);
+                fence_after_sync();
+                if (s == 15) {                                                    // the tile's copy has left P before `done` lets the next stage overwrite it
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                }
+                if (elect_one()) {
                     if (!lo) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_f16(T + cAcc + 128u * half, desc(sPlo + blk * kSlab + kk * 32u), desc(sB + kk * 32u), idesc_f16(128, 128, 0, 0), 1u);
+                        for (int kk = 0; kk < 2; ++kk) mma_f16(T + cAcc, dPlo + aoff + 2u * kk, dB + (uint64_t)(kk * 128), idFullT, kk ? 1u : later);
                     }
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        mma_f16(T + cAcc + 128u * half, desc(sPhi + blk * kSlab + kk * 32u), desc(sB + kk * 32u), idesc_f16(128, 128, 0, 0), 1u);
+                    for (int kk = 0; kk < 2; ++kk) mma_f16(T + cAcc, dPhi + aoff + 2u * kk, dB + (uint64_t)(kk * 128), idFullT, (kk || !lo) ? 1u : later);
                     mma_commit(&bars[BAR_EMPTY + slot]);
+                    if (s == 15) mma_commit(done);
                 }
-                bulk_wait_read();                                                 // the h1 tile has been read out of P: stage B may overwrite it
-                mma_commit(&bars[BAR_Z2]);
-                // ---- heads ----
-                mbar_wait(&bars[RDY_H2], p); fence_after_sync();
+                __syncwarp();
+            }
+        };
+        mbar_wait(&bars[RDY_X], 0); fence_after_sync();
+        issue_l1(0);
 #pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const uint32_t p = (uint32_t)i & 1u;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * G;
+            const uint64_t dXg = desc(sX + 32u * (1u + p));
+            const uint64_t dXgT = desc(sX + 32u * (1u + p), kSlab);
+            const uint32_t acc_w = (i % kFlushTiles) != 0 ? 1u : 0u;
+            // ---- forward: z2 = b2 + h1 . W2^T ----
+            GS_WT(1, 0);
+            mbar_wait(&bars[RDY_H1], p); fence_after_sync();
+            GS_WT(1, 1);
+            store_tile(tile, 0u);
+            if (elect_one()) mma_f16(T + cAcc, dXg, dWS + 4u, idFull, 0u);
+            __syncwarp();
+            gemm_phase(1u, &bars[BAR_Z2]);
+            GS_WT(1, 3);
+            // ---- heads ----
+            mbar_wait(&bars[RDY_H2], p); fence_after_sync();
+            GS_WT(1, 4);
+            if (elect_one()) {
+#pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t a0 = pass == 0 ? sPlo : sPhi;
-#pragma unroll 4
-                    for (int kk = 0; kk < 16; ++kk)
-                        mma_f16(T + cH, desc(a0 + kfeat(kk)), desc(sWS + 96u + (uint32_t)kk * 2048u, H * 128u), idesc_f16(128, 16, 0, 1), (pass | kk) ? 1u : 0u);
+                    const uint64_t a0 = pass == 0 ? dPlo : dPhi;
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) mma_f16(T + cH, a0 + kfeat(kk), dWSh + (uint64_t)(kk * 128), idHeads, (pass | kk) ? 1u : 0u);
                 }
                 mma_commit(&bars[BAR_OUT]);
-                // ---- dh2 = g16 . Wh ; W-c: dWh^T += h2^T g16 ----
-                mbar_wait(&bars[RDY_G], p); fence_after_sync();
-                mma_f16(T + cAcc, desc(sX), desc(sWS + 96u), idesc_f16(128, H, 0, 0), 0u);
-                mma_commit(&bars[BAR_DH2]);
-#pragma unroll 1
-                for (int mb = 0; mb < 2; ++mb)
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const uint32_t a0 = (pass == 0 ? sPlo : sPhi) + (uint32_t)mb * 2u * kSlab;
-#pragma unroll 4
-                        for (int kk = 0; kk < 8; ++kk)
-                            mma_f16(T + cWh + 16u * mb, desc(a0 + (uint32_t)kk * 2048u, kSlab), desc(sX + (uint32_t)kk * 2048u, kSlab), idesc_f16(128, 16, 1, 1),
-                                    (pass | kk) ? 1u : acc_w);
-                    }
-                mma_commit(&bars[BAR_WC]);
-                // ---- W-d: db2 += dz2^T [ones] ; dgrad: dh1 = dz2 . W2 ----
-                mbar_wait(&bars[RDY_DZ2], p); fence_after_sync();
-                store_tile(tile, 1u);
-#pragma unroll 1
-                for (int mb = 0; mb < 2; ++mb)
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const uint32_t a0 = (pass == 0 ? sPlo : sPhi) + (uint32_t)mb * 2u * kSlab;
-#pragma unroll 4
-                        for (int kk = 0; kk < 8; ++kk)
-                            mma_f16(T + cB2 + 16u * mb, desc(a0 + (uint32_t)kk * 2048u, kSlab), desc(sX + (uint32_t)kk * 2048u, kSlab), idesc_f16(128, 16, 1, 1),
-                                    (pass | kk) ? 1u : acc_w);
-                    }
-#pragma unroll 1
-                for (int s = 0; s < 16; ++s, ++q) {
-                    const uint32_t slot = q % kRing, round = q / kRing;
-                    const bool lo = s < 8;
-                    const uint32_t blk = (uint32_t)(s & 7) >> 1, half = (uint32_t)s & 1u;
-                    const uint32_t sB = sRing + slot * kStage;
-                    const uint32_t fresh = (s & 7) < 2 && lo ? 0u : 1u;           // the first block into each half of the accumulator
-                    mbar_wait(&bars[BAR_FULL + slot], round & 1u);
-                    fence_after_sync();
-                    if (!lo) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_f16(T + cAcc + 128u * half, desc(sPlo + blk * kSlab + kk * 32u), desc(sB + kk * 2048u, 8192u), idesc_f16(128, 128, 0, 1), 1u);
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        mma_f16(T + cAcc + 128u * half, desc(sPhi + blk * kSlab + kk * 32u), desc(sB + kk * 2048u, 8192u), idesc_f16(128, 128, 0, 1),
-                                kk ? 1u : fresh);
-                    mma_commit(&bars[BAR_EMPTY + slot]);
-                }
-                bulk_wait_read();
-                mma_commit(&bars[BAR_DH1]);
-                // ---- W-b: [dW1 | db1] += dz1^T x16 ; next tile's layer 1 ----
-                mbar_wait(&bars[RDY_DZ1], p); fence_after_sync();
-#pragma unroll 1
-                for (int mb = 0; mb < 2; ++mb)
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const uint32_t a0 = (pass == 0 ? sPlo : sPhi) + (uint32_t)mb * 2u * kSlab;
-#pragma unroll 4
-                        for (int kk = 0; kk < 8; ++kk)
-                            mma_f16(T + cW1 + 16u * mb, desc(a0 + (uint32_t)kk * 2048u, kSlab), desc(sXg + (uint32_t)kk * 2048u, kSlab), idesc_f16(128, 16, 1, 1),
-                                    (pass | kk) ? 1u : acc_w);
-                    }
-                mma_commit(&bars[BAR_WB]);
-                if (i + 1 < n_my) {
-                    mbar_wait(&bars[RDY_X], p ^ 1u); fence_after_sync();
-                    issue_l1(i + 1);
-                }
             }
-            bulk_wait_all();                                                      // the stored tiles are complete before the kernel ends
+            __syncwarp();
+            GS_WT(1, 5);
+            // ---- dh2 = g16 . Wh ; W-c: dWh^T += h2^T g16 ----
+            mbar_wait(&bars[RDY_G], p); fence_after_sync();
+            GS_WT(1, 6);
+            if (elect_one()) {
+                mma_f16(T + cAcc, desc(sX), dWS + 6u, idFull, 0u);
+                mma_commit(&bars[BAR_DH2]);
+                issue_wgrad16(cWh, dG, acc_w);
+                mma_commit(&bars[BAR_WC]);
+            }
+            __syncwarp();
+            GS_WT(1, 7);
+            // ---- W-d: db2 += dz2^T [ones] ; dgrad: dh1 = dz2 . W2 ----
+            mbar_wait(&bars[RDY_DZ2], p); fence_after_sync();
+            GS_WT(1, 8);
+            store_tile(tile, 1u);
+            if (elect_one()) issue_wgrad16(cB2, dG, acc_w);
+            __syncwarp();
+            gemm_phase(0u, &bars[BAR_DH1]);
+            GS_WT(1, 10);
+            // ---- W-b: [dW1 | db1] += dz1^T x16 ; next tile's layer 1 ----
+            mbar_wait(&bars[RDY_DZ1], p); fence_after_sync();
+            GS_WT(1, 11);
+            if (elect_one()) {
+                issue_wgrad16(cW1, dXgT, acc_w);
+                mma_commit(&bars[BAR_WB]);
+            }
+            __syncwarp();
+            GS_WT(1, 12);
+            if (i + 1 < n_my) {
+                mbar_wait(&bars[RDY_X], p ^ 1u); fence_after_sync();
+                issue_l1(i + 1);
+            }
+            GS_WT(1, 13);
         }
+        if (lane == 0) bulk_wait_all();                                           // the stored tiles are complete before the kernel ends
         return;
     }
 
@@ -456,8 +497,10 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         const uint32_t p = (uint32_t)i & 1u;
         const bool valid = tile_of(i) * kRows + row < b.n;
         // ---- A: h1 ----------------------------------------------------------------------------------------------------------
+        GS_WT(0, 0);
         mbar_wait(&bars[BAR_Z1], p);
         fence_after_sync();
+        GS_WT(0, 1);
         if (i > 0 && (i % kFlushTiles) == 0) {               // every weight-gradient MMA of the previous tiles has completed
             mbar_wait(&bars[BAR_WB], p ^ 1u);
             fence_after_sync();
@@ -465,15 +508,19 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         }
         const uint64_t mask1 = fwd_stage(valid, zs0, zq0, dead0, i > 0 ? &bars[BAR_WB] : nullptr, p ^ 1u);   // W-b(i-1) reads dz1 from P
         warp_ready(RDY_H1);
+        GS_WT(0, 2);
         // ---- B: h2 ----------------------------------------------------------------------------------------------------------
         mbar_wait(&bars[BAR_Z2], p);                          // every forward MMA is done and the h1 tile has been copied out of P
         fence_after_sync();
+        GS_WT(0, 3);
         const uint64_t mask2 = fwd_stage(valid, zs1, zq1, dead1, nullptr, 0u);
         warp_ready(RDY_H2);
+        GS_WT(0, 4);
         // ---- C: loss (one thread per row) ----------------------------------------------------------------------------------------
         if (loss_thread) {
             mbar_wait(&bars[BAR_OUT], p);
             fence_after_sync();
+            GS_WT(0, 5);
             float c[16];
             tmem_ld16(T + cH, c);
             const uint4 sc = *reinterpret_cast<const uint4*>(Xrow + ((6 ^ sw) << 4));
@@ -494,15 +541,18 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
             split_pair(g[2], g[3], h23, l23);
             *reinterpret_cast<uint4*>(Xrow + ((0 ^ sw) << 4)) = make_uint4(h01, h23, l01, l23);
             *reinterpret_cast<uint4*>(Xrow + ((1 ^ sw) << 4)) = make_uint4(h01, h23, 0u, kOnes2);
-            if (i + 1 < n_my) prefetch(i + 1, next_off, next_ok);
-            next_off = offset_of(i + 2, next_ok);
             warp_ready(RDY_G);
+            GS_WT(0, 6);
+            if (i + 1 < n_my) prefetch(i + 1, next_off, next_ok);   // off the critical path; the scalars of this tile were consumed above
+            next_off = offset_of(i + 2, next_ok);
         }
         // ---- D: dz2 (over h2, once W-c has read it) ----------------------------------------------------------------------------------
         mbar_wait(&bars[BAR_DH2], p);
         fence_after_sync();
+        GS_WT(0, 7);
         bwd_stage(mask2, &bars[BAR_WC], p);
         warp_ready(RDY_DZ2);
+        GS_WT(0, 8);
         // ---- E: dz1 (over dz2: dgrad, W-d and the tile store are done once dh1 is complete) ---------------------------------------------
         if (loss_thread && i + 1 < n_my) {                    // the next tile's record has landed: its layer 1 may start after W-b
             cp_async_wait_all();
@@ -512,8 +562,10 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         }
         mbar_wait(&bars[BAR_DH1], p);
         fence_after_sync();
+        GS_WT(0, 9);
         bwd_stage(mask1, nullptr, 0u);
         warp_ready(RDY_DZ1);
+        GS_WT(0, 10);
     }
     mbar_wait(&bars[BAR_WB], (uint32_t)(n_my - 1) & 1u);
     fence_after_sync();
@@ -659,7 +711,7 @@ wgrad_wide_kernel(const unsigned char* __restrict__ tiles, int64_t n, float* __r
 // ---- host launcher (called from update_kernels.cu) -------------------------------------------------------------------------------
 int64_t wide_scratch_bytes(int64_t max_batch) {
     const int64_t tiles = (max_batch + 127) / 128;
-    return 2ll * wfu::kW2Prec + tiles * (int64_t)wfu::kTileBytes;
+    return 4ll * wfu::kW2Prec + tiles * (int64_t)wfu::kTileBytes;
 }
 
 template <int ALGO>
@@ -668,7 +720,7 @@ int launch_update_wide(const MlpDev& md, const BatchDev& b, const HpDev& hp, boo
                        uint32_t* dead, int grid, cudaStream_t st) {
     using namespace wfu;
     unsigned char* w2s = reinterpret_cast<unsigned char*>(scratch);
-    unsigned char* tiles = w2s + 2 * kW2Prec;
+    unsigned char* tiles = w2s + 4 * kW2Prec;
     stage_w2_kernel<<<32, 256, 0, st>>>(md, w2s);
     GS_LAUNCH_CHECK();
     using KernelFn = void (*)(MlpDev, BatchDev, HpDev, const double*, const double*, const uint32_t*, const uint4*, const unsigned char*, unsigned char*,
@@ -688,3 +740,9 @@ template int launch_update_wide<ALGO_PPO>(const MlpDev&, const BatchDev&, const 
 template int launch_update_wide<ALGO_REINFORCE>(const MlpDev&, const BatchDev&, const HpDev&, bool, const double*, const double*, const uint32_t*, const void*, void*, float*, int64_t, double*, uint32_t*, int, cudaStream_t);
 
 }  // namespace gs
+
+#ifdef GS_WIDE_TRACE
+extern "C" int gs_debug_wide_trace(long long* host_out /* [2][24] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_wide_trace, sizeof(long long) * 48);
+}
+#endif
