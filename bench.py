@@ -127,11 +127,12 @@ def build_agent_for_bench(args, rank, world):
 def launches_per_step(cfg, world):
     """Engine kernels launched per training iteration (ours; torch's optimizer / bookkeeping kernels are not counted)."""
     n_mb = (int(cfg.n_envs) * int(cfg.n_steps)) // int(cfg.batch_size) * int(cfg.n_epochs)
-    tensor_path = tuple(cfg.hidden_dims) in ((64, 64), (128, 128))
+    wide = tuple(cfg.hidden_dims) == (256, 256)
+    tensor_path = tuple(cfg.hidden_dims) in ((64, 64), (128, 128), (256, 256))
     per_rollout = 1 + 2 + 1 + 2 + (1 if tensor_path else 0)   # collect, obs/reward moments, gae, adv/ret moments, rollout_pack
     # tensor path: gather pass (offsets + batch moments; all of a rollout's up front when sharded), update kernel,
     # gs_update_finish (reduction + NVLink gradient mean + metrics + clip + Adam).  FMA-pipe path: batch moments, update, finish.
-    per_mb = 3
+    per_mb = 5 if wide else 3           # 256 x 256: + stage_w2_kernel and wgrad_wide_kernel (csrc/update_wide.cu)
     return per_rollout + n_mb * per_mb
 
 
@@ -277,7 +278,7 @@ def kernel_rooflines(agent, cfg, dev):
     agent._pack_rollout(traj)          # as train_on_rollout does: 64-byte sample records for the tensor-core kernel's gather
     batches = [b for _, _, b in agent.minibatches(traj, 12345)][:8]
     hd = tuple(cfg.hidden_dims)
-    tensor_path = hd in ((64, 64), (128, 128)) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
+    tensor_path = hd in ((64, 64), (128, 128), (256, 256)) and os.environ.get("GS_UPDATE_IMPL", "tc") != "simt"
     if tensor_path:
         offs = torch.empty(len(batches), agent.local_batch_size, dtype=torch.int32, device=dev)
         mom = torch.zeros(len(batches), 6, dtype=torch.float64, device=dev)
@@ -292,20 +293,29 @@ def kernel_rooflines(agent, cfg, dev):
         it[0] += 1
 
     t = timed(one_update)
-    flops = FLOP_PER_SAMPLE_PASS.get(hd, 27264) * agent.local_batch_size
+    env = agent.get_env("train")
+    obs_dim, n_act = int(traj.tm["obs"].shape[-1]), int((getattr(env, "single_action_space", None) or env.action_space).n)
+    flop_per_sample = 6 * (obs_dim * hd[0] + hd[0] * hd[-1] + (n_act + 1) * hd[-1])      # 3 x forward flops
+    flops = FLOP_PER_SAMPLE_PASS.get(hd, flop_per_sample) * agent.local_batch_size if (obs_dim, n_act) == (4, 2) else flop_per_sample * agent.local_batch_size
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     tp = os.path.join(ROOT, "profiles", "traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures
     traffic_table = json.load(open(tp)) if os.path.exists(tp) else {}
     full_size = (int(cfg.n_steps), agent.local_n_envs, agent.local_batch_size) == (128, 65536, 1048576)   # the captures' launch sizes
     tr = lambda name: traffic_table.get(name, {}).get("dram_bytes_per_launch") if full_size else None
-    traffic = tr("update_f16_kernel" if tensor_path else "update_kernel")
+    traffic = tr(("update_wide_kernel" if hd == (256, 256) else "update_f16_kernel") if tensor_path else "update_kernel")
     if tensor_path:
         # tensor-pipe floor of a 128-sample tile from the measured per-instruction costs (probes/bf16_rate.cu, cycles per tcgen05.mma K=16:
         # M=128 N=16: 40, N=64: 50, N=128: 66; M=64 N=16: 25, N=64: 34, N=80: 42): 64x64: 93 MMAs = 3,464 cycles; 128x128: 141 MMAs
         tiles_per_sm = -(-(agent.local_batch_size // 128) // 148)
         tile_cycles = 3464.0 if hd == (64, 64) else (3 * 66 + 24 * 66 + 16 * 40 + 66 + 16 * 40 + 24 * 66 + 16 * 72 + 8 * 66 + 16 * 40)
+        kname = f"update_f16_kernel<{hd[0]}, PPO> (gs_ppo_step: tcgen05 kind::f16, fp16x3 split, TMEM accumulators)"
+        if hd == (256, 256):
+            # update_wide_kernel: 2 x 48 N=256 MMAs (128 cycles each) + bias / layer 1 / dh2 (4 x 128) + heads and three 16-column weight-gradient
+            # groups (4 x 32 x 40); wgrad_wide_kernel: 48 N=256 MMAs per tile
+            tile_cycles = 96 * 128 + 4 * 128 + 128 * 40 + 48 * 128
+            kname = "update_wide_kernel + wgrad_wide_kernel (gs_ppo_step for 256x256: tcgen05 kind::f16, fp16x3 split, W2 streamed by cp.async.bulk)"
         mma_floor_s = tiles_per_sm * tile_cycles / (peaks["sm_max_mhz"] * 1e6)
-        out["update"] = {"kernel": f"update_f16_kernel<{hd[0]}, PPO> (gs_ppo_step: tcgen05 kind::f16, fp16x3 split, TMEM accumulators)", "bound": "tensor",
+        out["update"] = {"kernel": kname, "bound": "tensor",
                          "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"],
                          "traffic": traffic,
                          "note": "achieved = algorithmic fp32 FLOP (fwd + dgrad + wgrad of the MLP, 27,264 per sample for 64x64) / average launch time of "

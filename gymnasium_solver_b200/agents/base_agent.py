@@ -404,8 +404,8 @@ class BaseAgent(nn.Module):
 
     def _pack_rollout(self, traj: DeviceTrajectory) -> None:
         """One 64-byte record per sample (gs_rollout_pack: the bf16x3 layer-1 operand row + the sample's scalars) so the tensor-core
-        update kernel copies a minibatch sample straight into its operand tile with one aligned access.  The 64x64 and 128x128
-        networks have that kernel (observations of up to 7 features); the buffer is reused across rollouts."""
+        update kernel copies a minibatch sample straight into its operand tile with one aligned access.  The 64x64, 128x128 and (relu)
+        256x256 networks have that kernel (observations of up to 7 features); the buffer is reused across rollouts."""
         if not self._tensor_path(traj.tm["obs"].shape[-1]) or "packed" in traj.tm:
             return
         total = traj.T * traj.n_envs
@@ -418,10 +418,13 @@ class BaseAgent(nn.Module):
         traj.tm["packed"] = buf
 
     def _tensor_path(self, obs_dim: Optional[int] = None) -> bool:
-        """Does csrc/update_f16.cu serve this network (mirrors update_kernels.cu::tensor_path_for)?  Those kernels read per-minibatch
+        """Does csrc/update_f16.cu / update_wide.cu serve this network (mirrors update_kernels.cu::tensor_path_for)?  Those kernels read per-minibatch
         offset buffers and rollout records; everything else runs the FMA-pipe kernel."""
-        if tuple(getattr(self.config, "hidden_dims", ())) not in ((64, 64), (128, 128)):
+        hd = tuple(getattr(self.config, "hidden_dims", ()))
+        if hd not in ((64, 64), (128, 128), (256, 256)):
             return False
+        if hd == (256, 256) and str(getattr(self.config, "activation", None) or "relu").lower() != "relu":
+            return False                # csrc/update_wide.cu keeps relu' as a bit mask; tanh at 256 x 256 runs the FMA-pipe kernel
         if os.environ.get("GS_UPDATE_IMPL", "tc") == "simt":
             return False
         if obs_dim is None:

@@ -36,7 +36,7 @@ for name, env, variant, iters in CASES:
     steps = int(cfg.n_envs) * int(cfg.n_steps)
     n_mb = steps // int(cfg.batch_size)
     hd = tuple(cfg.hidden_dims)
-    path = "tcgen05 (fp16x3)" if hd in ((64, 64), (128, 128)) else "fp32 FMA pipe"
+    path = "tcgen05 (fp16x3)" if hd in ((64, 64), (128, 128), (256, 256)) else "fp32 FMA pipe"
     print(f"| {name} | {int(cfg.n_envs):,} x {int(cfg.n_steps)} | {hd} | {int(agent.n_epochs)} x {n_mb} | {ms:.1f} | {steps / ms * 1e3 / 1e6:.1f} M | {path} |", flush=True)
     del agent
     torch.cuda.empty_cache()
