@@ -10,7 +10,7 @@
 //     pass ([128 j-rows][64 k] blocks: K-major B, N = 128) and 16 for dgrad (64 j-rows x two 64-column slabs: MN-major B, N = 128).
 //   * the layer-2 weight gradient needs a 256 x 256 fp32 accumulator = all 512 TMEM columns.  It gets its own kernel: the fused
 //     kernel stores the two operands of that product -- the h1 and dz2 tiles exactly as they sit in shared memory (256 KB per
-//     128-sample tile, `cp.async.bulk` shared -> global by the MMA warp while the next MMA group runs) -- and `wgrad_wide_kernel`
+//     128-sample tile, `cp.async.bulk` shared -> global issued by the MMA warp in 16 KB pieces between the stages of the GEMM phase that follows) -- and `wgrad_wide_kernel`
 //     streams them back (4-stage ring of 32-sample slices, both operands MN-major straight from the stored bytes) into
 //     dW2 = dz2^T . h1 with M = 2 x 128, N = 256.  Every other gradient (dW1, b1, b2, heads) is a 16-column accumulator of the
 //     fused kernel, as in update_f16.cu; b2's is dz2^T . [ones] (the ones of the g16 group).
@@ -216,17 +216,6 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
             }
             __syncwarp();
         };
-        auto store_tile = [&](int64_t tile, uint32_t which) {                     // P (hi, lo) -> scratch slot `which` (0: h1, 1: dz2)
-#ifndef GS_WIDE_NOSTORE
-            if (lane == 0) {
-                unsigned char* dst = tiles + (size_t)tile * kTileBytes + (size_t)which * 2u * kTile;
-#pragma unroll 1
-                for (uint32_t c = 0; c < 2u * kTile; c += 16384u) bulk_s2g(dst + c, sPhi + c, 16384u);   // P_lo directly follows P_hi
-                bulk_commit();
-            }
-            __syncwarp();
-#endif
-        };
         // 32 small MMAs of a 16-column weight-gradient accumulator: acc[mb] (+)= A^T(P) . B, both MN-major, K = the tile's 128 samples
         auto issue_wgrad16 = [&](uint32_t col, uint64_t dB, uint32_t acc_w) {
 #pragma unroll
@@ -240,9 +229,18 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         };
         // one GEMM phase: acc (+)= P . B over the 16 ring stages (B MN-major, N = 256, two k-steps per stage); `first_acc` = accumulate flag of
         // the phase's first MMA; the last stage also commits `done`
-        auto gemm_phase = [&](uint32_t first_acc, uint64_t* done) {
+        auto gemm_phase = [&](uint32_t first_acc, uint64_t* done, unsigned char* gdst) {
 #pragma unroll 1
             for (int s = 0; s < 16; ++s, ++q) {
+#ifndef GS_WIDE_NOSTORE
+                // The tile in P (h1, then dz2) leaves for the workspace in eight 16 KB pieces, one every two stages (P_lo directly follows
+                // P_hi): all eight at the phase's start cost the MMAs beside them 3 % more (shared-memory bandwidth; measured).
+                if (lane == 0 && (s & 1) == 0) {
+                    bulk_s2g(gdst + (uint32_t)(s >> 1) * 16384u, sPhi + (uint32_t)(s >> 1) * 16384u, 16384u);
+                    if (s == 14) bulk_commit();
+                }
+                __syncwarp();
+#endif
                 const uint32_t slot = q % kRing, round = q / kRing;
                 const int sr = (s + rot) & 15;
                 const bool lo = sr < 8;
@@ -282,10 +280,9 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
             GS_WT(1, 0);
             mbar_wait(&bars[RDY_H1], p); fence_after_sync();
             GS_WT(1, 1);
-            store_tile(tile, 0u);
             if (elect_one()) mma_f16(T + cAcc, dXg, dWS + 4u, idFull, 0u);
             __syncwarp();
-            gemm_phase(1u, &bars[BAR_Z2]);
+            gemm_phase(1u, &bars[BAR_Z2], tiles + (size_t)tile * kTileBytes);
             GS_WT(1, 3);
             // ---- heads ----
             mbar_wait(&bars[RDY_H2], p); fence_after_sync();
@@ -315,10 +312,9 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
             // ---- W-d: db2 += dz2^T [ones] ; dgrad: dh1 = dz2 . W2 ----
             mbar_wait(&bars[RDY_DZ2], p); fence_after_sync();
             GS_WT(1, 8);
-            store_tile(tile, 1u);
             if (elect_one()) issue_wgrad16(cB2, dG, acc_w);
             __syncwarp();
-            gemm_phase(0u, &bars[BAR_DH1]);
+            gemm_phase(0u, &bars[BAR_DH1], tiles + (size_t)tile * kTileBytes + 2u * kTile);
             GS_WT(1, 10);
             // ---- W-b: [dW1 | db1] += dz1^T x16 ; next tile's layer 1 ----
             mbar_wait(&bars[RDY_DZ1], p); fence_after_sync();

@@ -1,4 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/w5_gpu_tests.log 2>&1; tail -5 gpurun_out/w5_gpu_tests.log
-timeout 600 python bench.py --config c4_mcar --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/w5_bench_c4_mcar.json 2> gpurun_out/w5_bench_c4_mcar.err; tail -c 1500 gpurun_out/w5_bench_c4_mcar.json; tail -3 gpurun_out/w5_bench_c4_mcar.err
+timeout 600 python -m pytest tests/test_gpu_update.py -x -q > gpurun_out/w7_update_tests.log 2>&1; tail -2 gpurun_out/w7_update_tests.log
+timeout 600 python tests/dev_wide_check.py 19072 1048576 > gpurun_out/w2_check.log 2>&1; grep "rel L2" gpurun_out/w2_check.log
+GS_DEV_HIDDEN=256 timeout 300 python tests/dev_update_time.py --child > gpurun_out/w7_plain_update256.log 2>&1 && tail -1 gpurun_out/w7_plain_update256.log &&
+GS_DEV_HIDDEN=256 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"update_wide|wgrad_wide|stage_w2" -s 15 -c 3 -o gpurun_out/r2_update_wide -f python tests/dev_update_time.py --child > gpurun_out/w7_ncu_update256.log 2>&1
+tail -2 gpurun_out/w7_ncu_update256.log
