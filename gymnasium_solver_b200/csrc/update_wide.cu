@@ -416,63 +416,65 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[which]);
     };
-    auto store_half = [&](int half, const uint32_t (&hw)[16], const uint32_t (&lw)[16]) {
+    // 16 columns of the row as (hi, lo) -> P
+    auto store_q = [&](int qt, const uint32_t (&hw)[8], const uint32_t (&lw)[8]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t o = my_off + (uint32_t)(((4 * half + c) ^ sw) << 4);
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t o = my_off + (uint32_t)(((2 * qt + c) ^ sw) << 4);
             *reinterpret_cast<uint4*>(Phi + o) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
             *reinterpret_cast<uint4*>(Plo + o) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
         }
     };
-    // forward stage: the row's 64 pre-activations -> relu -> (hi, lo) -> P; returns the relu mask
+    // forward stage: the row's 64 pre-activations -> relu -> (hi, lo) -> P, 16 columns at a time (the whole row in registers spilled);
+    // returns the relu mask
     auto fwd_stage = [&](bool valid, float& zs, float& zq, uint32_t (&dcnt)[2], uint64_t* release, uint32_t parity) -> uint64_t {
         uint64_t mask = 0ull;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float z[32];
-            tmem_ld32(T + cAcc + 64 * cg + 32 * half, z);
+        for (int qt = 0; qt < 4; ++qt) {
+            float z[16];
+            tmem_ld16(T + cAcc + 64 * cg + 16 * qt, z);
             tmem_ld_wait();
             if (TRACK) {
                 float mn = 1.0f;
                 if (valid) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) { zs += z[q]; zq = fmaf(z[q], z[q], zq); mn = fminf(mn, fabsf(z[q])); }
+                    for (int q = 0; q < 16; ++q) { zs += z[q]; zq = fmaf(z[q], z[q], zq); mn = fminf(mn, fabsf(z[q])); }
                 }
                 if (__any_sync(0xffffffffu, mn < 1e-6f)) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
+                    for (int q = 0; q < 16; ++q) {
                         const uint32_t hits = __popc(__ballot_sync(0xffffffffu, valid && fabsf(z[q]) < 1e-6f));
-                        if (lane == q) dcnt[half] += hits;
+                        if (lane == 16 * (qt & 1) + q) dcnt[qt >> 1] += hits;
                     }
                 }
             }
             uint32_t bits = 0u;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) bits |= (z[q] > 0.f ? 1u : 0u) << q;
-            mask |= (uint64_t)bits << (32 * half);
-            uint32_t hw[16], lw[16];
+            for (int q = 0; q < 16; ++q) bits |= (z[q] > 0.f ? 1u : 0u) << q;
+            mask |= (uint64_t)bits << (16 * qt);
+            uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) split_pair(fmaxf(z[2 * e], 0.f), fmaxf(z[2 * e + 1], 0.f), hw[e], lw[e]);
-            if (half == 0 && release) mbar_wait(release, parity);
-            store_half(half, hw, lw);
+            for (int e = 0; e < 8; ++e) split_pair(fmaxf(z[2 * e], 0.f), fmaxf(z[2 * e + 1], 0.f), hw[e], lw[e]);
+            if (qt == 0 && release) mbar_wait(release, parity);
+            store_q(qt, hw, lw);
         }
         return mask;
     };
     // backward stage: d(loss)/d(activation) of the row * relu' -> (hi, lo) -> P
     auto bwd_stage = [&](uint64_t mask, uint64_t* release, uint32_t parity) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float d[32];
-            tmem_ld32(T + cAcc + 64 * cg + 32 * half, d);
+        for (int qt = 0; qt < 4; ++qt) {
+            float d[16];
+            tmem_ld16(T + cAcc + 64 * cg + 16 * qt, d);
             tmem_ld_wait();
-            const uint32_t bits = (uint32_t)(mask >> (32 * half));
+            const uint32_t bits = (uint32_t)(mask >> (16 * qt));
 #pragma unroll
-            for (int q = 0; q < 32; ++q) d[q] = (bits >> q) & 1u ? d[q] : 0.f;
-            uint32_t hw[16], lw[16];
+            for (int q = 0; q < 16; ++q) d[q] = (bits >> q) & 1u ? d[q] : 0.f;
+            uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) split_pair(d[2 * e], d[2 * e + 1], hw[e], lw[e]);
-            if (half == 0 && release) mbar_wait(release, parity);
-            store_half(half, hw, lw);
+            for (int e = 0; e < 8; ++e) split_pair(d[2 * e], d[2 * e + 1], hw[e], lw[e]);
+            if (qt == 0 && release) mbar_wait(release, parity);
+            store_q(qt, hw, lw);
         }
     };
 
