@@ -30,18 +30,27 @@ gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, 
     float g = 0.0f;
     float vnext = __ldg(last_values + n);
     int t = T - 1;
-    for (; t >= kUnroll - 1; t -= kUnroll) {
-        float v[kUnroll], r[kUnroll], bt[kUnroll];
-        uint8_t d[kUnroll], to[kUnroll];
+    // software-pipelined: the loads of the NEXT kUnroll timesteps are issued before the (sequential, ~50-cycle-per-step) recurrence over the
+    // current ones, so a thread keeps 2 x kUnroll timesteps of loads in flight -- at C2 an SM holds only ~14 warps of this kernel
+    float v[kUnroll], r[kUnroll], bt[kUnroll];
+    uint8_t d[kUnroll], to[kUnroll];
+    auto load = [&](int t0, float (&v_)[kUnroll], float (&r_)[kUnroll], float (&bt_)[kUnroll], uint8_t (&d_)[kUnroll], uint8_t (&to_)[kUnroll]) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t o = (int64_t)(t - u) * N + n;
-            v[u] = ldg_stream(values + o);
-            r[u] = ldg_stream(rewards + o);
-            d[u] = ldg_stream(dones + o);
-            to[u] = ldg_stream(timeouts + o);
-            bt[u] = BOOT == 1 ? ldg_stream(boot + o) : 0.0f;
+            const int64_t o = (int64_t)(t0 - u) * N + n;
+            v_[u] = ldg_stream(values + o);
+            r_[u] = ldg_stream(rewards + o);
+            d_[u] = ldg_stream(dones + o);
+            to_[u] = ldg_stream(timeouts + o);
+            bt_[u] = BOOT == 1 ? ldg_stream(boot + o) : 0.0f;
         }
+    };
+    if (t >= kUnroll - 1) load(t, v, r, bt, d, to);
+    for (; t >= kUnroll - 1; t -= kUnroll) {
+        float v2[kUnroll], r2[kUnroll], bt2[kUnroll];
+        uint8_t d2[kUnroll], to2[kUnroll];
+        const bool more = t - kUnroll >= kUnroll - 1;
+        if (more) load(t - kUnroll, v2, r2, bt2, d2, to2);
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t o = (int64_t)(t - u) * N + n;
@@ -52,6 +61,10 @@ gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, 
             stg_stream(adv + o, g);
             stg_stream(ret + o, fadd(g, v[u]));
             vnext = v[u];
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) { v[u] = v2[u]; r[u] = r2[u]; bt[u] = bt2[u]; d[u] = d2[u]; to[u] = to2[u]; }
         }
     }
     for (; t >= 0; --t) {
