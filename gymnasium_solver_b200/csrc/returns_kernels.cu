@@ -91,22 +91,34 @@ mc_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, 
     float acc = 0.0f;
     int32_t last = -1;
     int t = T - 1;
-    for (; t >= kUnroll - 1; t -= kUnroll) {
-        float r[kUnroll];
-        uint8_t d[kUnroll], to[kUnroll];
+    // software-pipelined like gae_kernel: the next batch's loads are in flight during this batch's recurrence
+    float r[kUnroll];
+    uint8_t d[kUnroll], to[kUnroll];
+    auto load = [&](int t0, float (&r_)[kUnroll], uint8_t (&d_)[kUnroll], uint8_t (&to_)[kUnroll]) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t o = (int64_t)(t - u) * N + n;
-            r[u] = ldg_stream(rewards + o);
-            d[u] = ldg_stream(dones + o);
-            to[u] = HAS_TO ? ldg_stream(timeouts + o) : (uint8_t)0;
+            const int64_t o = (int64_t)(t0 - u) * N + n;
+            r_[u] = ldg_stream(rewards + o);
+            d_[u] = ldg_stream(dones + o);
+            to_[u] = HAS_TO ? ldg_stream(timeouts + o) : (uint8_t)0;
         }
+    };
+    if (t >= kUnroll - 1) load(t, r, d, to);
+    for (; t >= kUnroll - 1; t -= kUnroll) {
+        float r2[kUnroll];
+        uint8_t d2[kUnroll], to2[kUnroll];
+        const bool more = t - kUnroll >= kUnroll - 1;
+        if (more) load(t - kUnroll, r2, d2, to2);
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const bool term = d[u] && !to[u];
             if (term && last < 0) last = t - u;
             acc = fadd(r[u], fmul(gamma, fmul(acc, term ? 0.0f : 1.0f)));
             ret[(int64_t)(t - u) * N + n] = acc;
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) { r[u] = r2[u]; d[u] = d2[u]; to[u] = to2[u]; }
         }
     }
     for (; t >= 0; --t) {

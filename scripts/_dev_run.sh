@@ -1,8 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_returns.py tests/test_gpu_fullsize.py -x -q > gpurun_out/w8_returns_tests.log 2>&1; tail -2 gpurun_out/w8_returns_tests.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/w8_bench_c2.json 2> gpurun_out/w8_bench_c2.err; python - <<'PY'
-import json
-d=[json.loads(l) for l in open("gpurun_out/w8_bench_c2.json") if l.startswith("{")][-1]
-print(d["value"]/1e6, d["ms_per_step"], d["roofline_gae"], d["roofline"]["avg_launch_s"], d["roofline_collect"]["avg_call_s"])
-PY
+cp gymnasium_solver_b200/csrc/libgs_engine.so /tmp/orig.so
+for v in u8 u16; do cp _exp/$v.so gymnasium_solver_b200/csrc/libgs_engine.so; echo "== $v"; timeout 600 python scripts/microbench_sweep.py --min-log2 12 2>&1 | cut -d'|' -f1-10; done > gpurun_out/w9_sweep.log 2>&1
+cp /tmp/orig.so gymnasium_solver_b200/csrc/libgs_engine.so
+timeout 600 python -m pytest tests/test_gpu_returns.py -x -q 2>&1 | tail -1
+cat gpurun_out/w9_sweep.log
