@@ -180,6 +180,14 @@ def run_b200(args):
     ms_total = float(ms.item())
     value = steps_per_iter_local * world * args.steps / (ms_total * 1e-3)
     agent.pop_epoch_metrics()
+    if os.environ.get("GS_DEV_FINISH_TRACE"):     # development builds (-DGS_FINISH_TRACE): per-phase time of the step tail's last block
+        import ctypes
+        from gymnasium_solver_b200 import _native as _N
+        buf = (ctypes.c_ulonglong * 8)()
+        ctypes.CDLL(_N.LIB_PATH).gs_debug_finish_trace(buf)
+        n_calls = max(1, int(buf[7]))
+        print(f"[finish trace] rank {rank}: calls {n_calls}, ns per call: phaseA-all-blocks {buf[0] / n_calls:.0f}, flags {buf[1] / n_calls:.0f}, "
+              f"slot-sum {buf[2] / n_calls:.0f}, metrics+norms+adam {buf[3] / n_calls:.0f}", file=sys.stderr, flush=True)
 
     # ---- e2e: public API + per-step H2D of the hyper-parameter block and D2H of metrics / episode stats / weights ------
     num = lambda name: float(getattr(cfg, name, 0.0) or 0.0) if not isinstance(getattr(cfg, name, 0.0), dict) else 0.0

@@ -443,8 +443,7 @@ __global__ void reduce_and_finalize_kernel(const float* __restrict__ partials, i
 // ---- fused step tail (gs_update_finish): partial reduction -> NVLink gradient exchange -> metrics -> clip -> Adam ----------
 struct PeerDev {
     int rank, world;
-    float* slots[GS_PEER_MAX_WORLD];      // slots[r]: rank r's receive buffer [2 phases][world][stride] (peer-mapped)
-    uint32_t* flags[GS_PEER_MAX_WORLD];   // flags[r]: rank r's arrival flags  [2 phases][world]
+    unsigned long long* slots[GS_PEER_MAX_WORLD];   // slots[r]: rank r's receive buffer [2 phases][world][stride] of {value bits, epoch} words (peer-mapped)
     uint32_t epoch;                       // call counter (>= 1), identical on every rank
     int64_t stride;
 };
@@ -456,13 +455,26 @@ struct FinishDev {
     const uint32_t* dead; uint32_t* ticket;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// The exchange carries its own arrival flags: every gradient element travels as ONE 8-byte word {fp32 bits, call epoch} (an aligned 8-byte store
+// is not torn), so the receiver polls the data itself -- no system-wide fence after the stores, no separate flag store behind a release, no
+// second NVLink round trip (the protocol NCCL calls LL).  Measured on 2 GPUs with per-phase globaltimer stamps: fenced stores + flag exchange
+// cost 12 + 8 us per minibatch in the step tail against 6 us for the same phase on one GPU.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
+#ifdef GS_FINISH_TRACE   // development aid: globaltimer (ns) sums over calls of the last block's phases; gs_debug_finish_trace() reads them
+__device__ unsigned long long g_fin_trace[8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GS_FT(k) do { if (tid == 0) { const unsigned long long now_ = gtime(); atomicAdd(&g_fin_trace[k], now_ - t_prev_); t_prev_ = now_; } } while (0)
+#else
+#define GS_FT(k) do { } while (0)
+#endif
 constexpr int kFinishThreads = 1024;    // phase A: 64 parameters x 16 groups of partial vectors per block
 constexpr int kFinishGroups = kFinishThreads / 64;
 __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad, PeerDev peer,
@@ -473,6 +485,9 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     __shared__ int is_last;
     const int tid = threadIdx.x;
     const int phase = (int)(peer.epoch & 1u);
+#ifdef GS_FINISH_TRACE
+    unsigned long long t_prev_ = gtime();
+#endif
     // programmatic dependent launch: the next minibatch's update kernel may be scheduled now; it runs its weight-independent
     // prologue and then blocks in griddepcontrol.wait until this grid has completed and flushed (parameters, moments, ticket)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -508,40 +523,48 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
             }
             if (peer.world > 1) {
                 const int64_t o = ((int64_t)phase * peer.world + peer.rank) * peer.stride + i;
-                for (int r = 0; r < peer.world; ++r) peer.slots[r][o] = s;
+                const unsigned long long word = ((unsigned long long)peer.epoch << 32) | (unsigned long long)__float_as_uint(s);
+                for (int r = 0; r < peer.world; ++r) st_relaxed_sys_u64(peer.slots[r] + o, word);
             } else {
                 grads[i] = s;
             }
         }
     }
-    if (peer.world > 1) __threadfence_system(); else __threadfence();
+    if (peer.world == 1) __threadfence();                       // several ranks: the last block polls the words themselves
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    GS_FT(0);                                                  // entry of the last block -> every block's phase A done
     // ---- phase B (the last block to arrive) -----------------------------------------------------------------------------------
     if (peer.world > 1) {
-        // st.release.sys is cumulative: the other blocks' slot stores (each fenced system-wide before its ticket, observed through the
-        // ticket + __threadfence above) are ordered before the flag -- no second system fence here
-        if (tid < peer.world) st_release_sys(peer.flags[tid] + phase * peer.world + peer.rank, peer.epoch);
-        if (tid < peer.world) {
-            const uint32_t* fl = peer.flags[peer.rank] + phase * peer.world + tid;
-            uint32_t spin = 0;
-            while (ld_acquire_sys(fl) != peer.epoch) {
-                if (++spin > (1u << 28)) __trap();              // a rank left the lock-step call sequence: fail, do not hang
-                __nanosleep(32);
-            }
-        }
-        __syncthreads();
-        const float* mine = peer.slots[peer.rank] + (int64_t)phase * peer.world * peer.stride;
+        // every rank's word of element i, in rank order (every rank computes the bit-identical mean); a word is valid once it carries this
+        // call's epoch.  Bounded spin -> trap: a rank left the lock-step call sequence (fail, do not hang).
+        const unsigned long long* mine = peer.slots[peer.rank] + (int64_t)phase * peer.world * peer.stride;
         const float inv_w = 1.0f / (float)peer.world;
         for (int64_t i = tid; i < f.P; i += kFinishThreads) {
+            unsigned long long w[GS_PEER_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < GS_PEER_MAX_WORLD; ++r)          // all ranks' words requested at once
+                if (r < peer.world) w[r] = ld_relaxed_sys_u64(mine + (int64_t)r * peer.stride + i);
             float s = 0.f;
-            for (int r = 0; r < peer.world; ++r) s += __ldcg(mine + (int64_t)r * peer.stride + i);   // rank order: identical on every rank
+#pragma unroll
+            for (int r = 0; r < GS_PEER_MAX_WORLD; ++r) {
+                if (r < peer.world) {
+                    uint32_t spin = 0;
+                    while ((uint32_t)(w[r] >> 32) != peer.epoch) {
+                        if (++spin > (1u << 27)) __trap();
+                        __nanosleep(20);
+                        w[r] = ld_relaxed_sys_u64(mine + (int64_t)r * peer.stride + i);
+                    }
+                    s += __uint_as_float((uint32_t)w[r]);
+                }
+            }
             grads[i] = s * inv_w;
         }
         __syncthreads();
+        GS_FT(2);                                              // every rank's words received and summed
     }
     // metric vector of the step (slots below GS_M_GRAD_NORM_ALL, batch count, return-normalisation slots)
     finalize_metrics_body(f.metric_partials, f.n_metric_cta, f.algo, f.H1, f.H2, f.track, f.vf_coef, f.ent_coef, f.normalize_adv, f.normalize_ret,
@@ -593,6 +616,10 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
         for (int64_t i = tid; i < po.total; i += kFinishThreads) grads[i] = __ldcg(grads + i) * c;
     }
     __syncthreads();
+    GS_FT(3);                                                  // metrics, norms, clip, Adam
+#ifdef GS_FINISH_TRACE
+    if (tid == 0) atomicAdd(&g_fin_trace[7], 1ull);
+#endif
     if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
 }
 
@@ -1048,12 +1075,12 @@ int gs_clip_grad_norm(const gs_mlp_t* mlp, float* grads_flat, float max_norm, do
 struct gs_peer {
     int rank = 0, world = 1, device = 0;
     int64_t stride = 0;                 // floats per slot (16-byte multiple)
-    void* base = nullptr;               // own allocation: [2][world][stride] floats, then [2][world] u32 flags
+    void* base = nullptr;               // own allocation: [2 phases][world][stride] 8-byte words {value bits, epoch}
     void* mapped[GS_PEER_MAX_WORLD] = {};   // peers' allocations (own rank: base)
     bool connected = false;
     uint32_t epoch = 0;
 };
-static size_t peer_slot_bytes(const gs_peer* p) { return ((size_t)2 * p->world * p->stride * 4 + 255) / 256 * 256; }
+static size_t peer_slot_bytes(const gs_peer* p) { return ((size_t)2 * p->world * p->stride * 8 + 255) / 256 * 256; }
 
 int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_peer_t** out, void* handle_out_host) {
     if (!out || !handle_out_host) GS_FAIL("gs_peer_create: NULL argument");
@@ -1151,10 +1178,7 @@ int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_fini
         if (f.pstride > peer->stride) GS_FAIL("gs_update_finish: peer slots hold %lld floats, the model has %lld", (long long)peer->stride, (long long)P);
         pd.rank = peer->rank; pd.world = peer->world; pd.stride = peer->stride;
         pd.epoch = ++peer->epoch;
-        for (int r = 0; r < peer->world; ++r) {
-            pd.slots[r] = (float*)peer->mapped[r];
-            pd.flags[r] = (uint32_t*)((char*)peer->mapped[r] + peer_slot_bytes(peer));
-        }
+        for (int r = 0; r < peer->world; ++r) pd.slots[r] = (unsigned long long*)peer->mapped[r];
     }
     const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
     const unsigned blocks = (unsigned)((P + 63) / 64);
@@ -1176,3 +1200,9 @@ int gs_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, fl
 }
 
 }  // extern "C"
+
+#ifdef GS_FINISH_TRACE
+extern "C" int gs_debug_finish_trace(unsigned long long* host_out /* [8] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, gs::g_fin_trace, sizeof(unsigned long long) * 8);
+}
+#endif

@@ -1,7 +1,11 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 cp gymnasium_solver_b200/csrc/libgs_engine.so /tmp/orig.so
-for v in u8 u16; do cp _exp/$v.so gymnasium_solver_b200/csrc/libgs_engine.so; echo "== $v"; timeout 600 python scripts/microbench_sweep.py --min-log2 12 2>&1 | cut -d'|' -f1-10; done > gpurun_out/w9_sweep.log 2>&1
+for v in old new old new; do
+  cp _exp/$v.so gymnasium_solver_b200/csrc/libgs_engine.so
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  python -c "
+import json
+d=[json.loads(l) for l in open('gpurun_out/ab_$v.json') if l.startswith('{')][-1]; print('$v', round(d['value']/1e6,1), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']/1e6,1))"
+done
 cp /tmp/orig.so gymnasium_solver_b200/csrc/libgs_engine.so
-timeout 600 python -m pytest tests/test_gpu_returns.py -x -q 2>&1 | tail -1
-cat gpurun_out/w9_sweep.log

@@ -25,7 +25,8 @@ def stress(rank, world, dev):
 
     cfg = load_config("CartPole-v1", "ppo")
     cfg.n_envs, cfg.n_steps, cfg.batch_size, cfg.n_epochs = 128 * world, 32, 4096 * world, 1
-    cfg.model_id, cfg._hidden_dims = "mlp_medium", resolve_model_spec("mlp_medium").hidden_dims   # 256x256 (FMA-pipe kernel): gradients live in grads_flat
+    cfg.model_id, cfg._hidden_dims = "mlp_medium", resolve_model_spec("mlp_medium").hidden_dims
+    cfg._activation = "tanh"          # 256x256 tanh runs the FMA-pipe kernel (atomic accumulation): gs_update_finish takes the gradients from grads_flat
     cfg.eval_freq_epochs, cfg.grad_allreduce = None, "peer"
     cfg.validate()
     agent = build_agent(cfg, rank=rank, world_size=world)
@@ -58,18 +59,20 @@ def training(rank, world, dev):
     from gymnasium_solver_b200.utils.config import load_config
     from gymnasium_solver_b200.utils.model_registry import resolve_model_spec
 
-    def make(mode, model_id):
+    def make(mode, model_id, activation):
         cfg = load_config("CartPole-v1", "ppo")
         cfg.n_envs, cfg.n_steps, cfg.batch_size, cfg.n_epochs = 256 * world, 32, 2048 * world, 3
         cfg.model_id, cfg._hidden_dims = model_id, resolve_model_spec(model_id).hidden_dims
+        cfg._activation = activation
         cfg.eval_freq_epochs = None
         cfg.grad_allreduce = mode
         cfg.fused_update = mode == "peer"
         cfg.validate()
         return build_agent(cfg, rank=rank, world_size=world)
 
-    for model_id in ("mlp_64x64", "mlp_small", "mlp_medium"):     # two-set / one-set tensor-core kernels, FMA-pipe kernel
-        a, b = make("peer", model_id), make("nccl", model_id)
+    # two-set / one-set tensor-core kernels, the 256-wide pair of kernels (update_wide.cu), the FMA-pipe kernel
+    for model_id, activation in (("mlp_64x64", "relu"), ("mlp_small", "relu"), ("mlp_medium", "relu"), ("mlp_medium", "tanh")):
+        a, b = make("peer", model_id, activation), make("nccl", model_id, activation)
         assert a._peer is not None and a.grad_allreduce_mode == "peer" and b._peer is None and b.grad_allreduce_mode == "nccl"
         for it in range(4):
             # identical state before the iteration: weights, Adam moments, step count (envs and RNG counters evolve identically)
