@@ -349,8 +349,8 @@ typedef struct gs_finish {
     int32_t reserved_;
 } gs_finish_t;
 
-/* NVLink peer group for the gradient exchange: every rank allocates one device buffer of receive slots + flags
- * (gs_peer_create), the 64-byte CUDA IPC handles are exchanged by the caller (any host channel, e.g. an all_gather over
+/* NVLink peer group for the gradient exchange: every rank allocates one device buffer of receive slots -- [2 phases][world_size][max_floats]
+ * 8-byte words {fp32 bits, call epoch}: the data carries its own arrival flags -- (gs_peer_create), the 64-byte CUDA IPC handles are exchanged by the caller (any host channel, e.g. an all_gather over
  * the torch.distributed store), gs_peer_connect maps the other ranks' buffers.  world_size <= 8 (one NVSwitch domain). */
 typedef struct gs_peer gs_peer_t;
 #define GS_PEER_HANDLE_BYTES 64
