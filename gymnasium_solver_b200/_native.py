@@ -128,6 +128,7 @@ SIGNATURES = {
     "gs_peer_create": (_i32, [_i32, _i32, _i64, _i32, C.POINTER(_vp), _vp]),
     "gs_peer_connect": (_i32, [_vp, _vp]),
     "gs_peer_destroy": (_i32, [_vp]),
+    "gs_peer_allreduce_f64": (_i32, [_vp, _vp, _i64, _vp]),
     "gs_update_finish": (_i32, [C.POINTER(GsMlp), C.POINTER(GsBatch), C.POINTER(GsFinish), _vp, C.POINTER(GsAdam), _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 

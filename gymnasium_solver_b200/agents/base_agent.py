@@ -309,7 +309,7 @@ class BaseAgent(nn.Module):
             return None
         if b.moments is None:
             self._prepare(b, self._mom_scratch)
-            allreduce_moments(self._mom_scratch, self.world_size)
+            allreduce_moments(self._mom_scratch, self.world_size, peer=self._peer)
         return b.moments
 
     def _fused_step_ok(self, batch) -> bool:
@@ -448,7 +448,7 @@ class BaseAgent(nn.Module):
             if offs is not None:
                 b.struct.offsets = N.ptr(offs[k])
             self._prepare(b, mom[k])
-        allreduce_moments(mom, self.world_size)
+        allreduce_moments(mom, self.world_size, peer=self._peer)
 
     def train_on_rollout(self, traj: DeviceTrajectory) -> None:
         self._early_stop_epoch = False
@@ -493,7 +493,7 @@ class BaseAgent(nn.Module):
                 b.struct.offsets = N.ptr(st["offs"][(c & 1) * per_pass + (k - lo)])
                 self._prepare(b, st["mom"][k])
                 if k == hi - 1:
-                    allreduce_moments(st["mom"][lo:hi], self.world_size)   # statistics of the GLOBAL minibatches of this pass
+                    allreduce_moments(st["mom"][lo:hi], self.world_size, peer=self._peer)   # statistics of the GLOBAL minibatches of this pass
                     st["ready"][c].record(side)
 
         side.wait_stream(main)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(CSRC, "libgs_engine.so")
-SOURCES = ["common.cu", "env_kernels.cu", "rollout_kernels.cu", "returns_kernels.cu", "update_kernels.cu", "update_f16.cu", "update_wide.cu", "collect_f16.cu"]
+SOURCES = ["common.cu", "env_kernels.cu", "rollout_kernels.cu", "returns_kernels.cu", "update_kernels.cu", "update_f16.cu", "update_wide.cu", "collect_f16.cu", "collect_wide.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr",

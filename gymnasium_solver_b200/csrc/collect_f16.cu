@@ -1,5 +1,5 @@
 // collect_f16.cu — the fused collect kernel and policy_act with the MLP forward on the tensor cores (fp16x3, see f16x3.cuh), for the
-// H x H networks update_f16.cu serves (H = 64, 128; observations of up to 7 features).
+// H x H networks update_f16.cu serves (H = 64, 128; observations of up to 7 features); H = 256 is dispatched to collect_wide.cu.
 //
 // Replaces, like rollout_kernels.cu: utils/policy_ops.py:14-41 (policy_act, policy_predict_values) and the per-step body of
 // RolloutCollector._collect (utils/rollout_collector.py:474-542) + RolloutBuffer.add (utils/rollout_buffer.py:82-102).
@@ -313,8 +313,13 @@ collect_f16_kernel(EnvDev h, MlpDev m, RolloutDev buf, float* __restrict__ cur_o
 bool f16_rollout_path(const gs_mlp_t* m) {
     const char* e = getenv("GS_ROLLOUT_IMPL");
     if (e && strcmp(e, "simt") == 0) return false;
-    return m->hidden1 == m->hidden2 && (m->hidden1 == 64 || m->hidden1 == 128) && m->obs_dim <= hfu::kMaxD;
+    return m->hidden1 == m->hidden2 && (m->hidden1 == 64 || m->hidden1 == 128 || m->hidden1 == 256) && m->obs_dim <= hfu::kMaxD;
 }
+// 256 x 256: collect_wide.cu (W2 streamed)
+int launch_collect_wide(gs_env* env, const MlpDev& md, const RolloutDev& buf, float* cur_obs, uint64_t seed, uint64_t step0, int deterministic,
+                        cudaStream_t st);
+int launch_policy_act_wide(const MlpDev& md, const float* obs, int64_t n, uint64_t seed, uint64_t offset, int64_t row_offset, int deterministic,
+                           const float* uniforms, int32_t* actions, float* logp, float* value, float* logits, cudaStream_t st);
 
 template <int H, int KIND>
 static int launch_collect_hk(gs_env* env, const MlpDev& md, const RolloutDev& buf, float* cur_obs, uint64_t seed, uint64_t step0, int deterministic,
@@ -332,6 +337,7 @@ static int launch_collect_hk(gs_env* env, const MlpDev& md, const RolloutDev& bu
 int launch_collect_f16(gs_env* env, const MlpDev& md, const RolloutDev& buf, float* cur_obs, uint64_t seed, uint64_t step0, int deterministic,
                        cudaStream_t st) {
 #define GS_CF(H, K) return launch_collect_hk<H, K>(env, md, buf, cur_obs, seed, step0, deterministic, st)
+    if (md.H1 == 256) return launch_collect_wide(env, md, buf, cur_obs, seed, step0, deterministic, st);
     if (md.H1 == 64) {
         if (env->kind == GS_ENV_CARTPOLE_V1) GS_CF(64, GS_ENV_CARTPOLE_V1);
         if (env->kind == GS_ENV_ACROBOT_V1) GS_CF(64, GS_ENV_ACROBOT_V1);
@@ -359,6 +365,7 @@ static int launch_act_h(const MlpDev& md, const cfu::ActDev& act, uint64_t seed,
 
 int launch_policy_act_f16(const MlpDev& md, const float* obs, int64_t n, uint64_t seed, uint64_t offset, int64_t row_offset, int deterministic,
                           const float* uniforms, int32_t* actions, float* logp, float* value, float* logits, cudaStream_t st) {
+    if (md.H1 == 256) return launch_policy_act_wide(md, obs, n, seed, offset, row_offset, deterministic, uniforms, actions, logp, value, logits, st);
     int device = 0;
     GS_CUDA(cudaGetDevice(&device));
     cfu::ActDev act;

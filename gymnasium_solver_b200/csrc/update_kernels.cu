@@ -453,6 +453,7 @@ struct FinishDev {
     const double* metric_partials; int n_metric_cta;
     int algo, H1, H2, track, normalize_adv, normalize_ret; float vf_coef, ent_coef, max_norm;
     const uint32_t* dead; uint32_t* ticket;
+    int split;                  // large models: this kernel only reduces + posts; finish_receive_kernel / finish_apply_kernel do the rest grid-wide
 };
 
 // The exchange carries its own arrival flags: every gradient element travels as ONE 8-byte word {fp32 bits, call epoch} (an aligned 8-byte store
@@ -535,6 +536,7 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     if (tid == 0) is_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
+    if (f.split) { if (tid == 0) *f.ticket = 0u; return; }
     __threadfence();
     GS_FT(0);                                                  // entry of the last block -> every block's phase A done
     // ---- phase B (the last block to arrive) -----------------------------------------------------------------------------------
@@ -621,6 +623,153 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
     if (tid == 0) atomicAdd(&g_fin_trace[7], 1ull);
 #endif
     if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
+}
+
+// ---- the step tail of LARGE models, grid-wide (P > kFinishSplitP) ---------------------------------------------------------------------
+// One block finishing a 68 k-parameter model (256 x 256) took 137 us per minibatch -- 7 % of a MountainCar-v0 iteration, and more than the
+// sharded update kernel itself at 8 GPUs.  update_finish_kernel then only reduces the partial vectors (and posts the words to the peers);
+//   finish_receive_kernel: every block receives / reads its 1024 gradient elements and writes the squared-norm partials of the three groups;
+//   finish_apply_kernel:   every block sums those partials in block order (identical everywhere), clips and applies Adam to its elements;
+//                          block 0 also finalises the metric vector.
+constexpr int64_t kFinishSplitP = 8192;
+__global__ void __launch_bounds__(kFinishThreads) finish_receive_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad, PeerDev peer,
+                                                                        double* __restrict__ sq_part /* [gridDim.x][3] + step snapshot */) {
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kFinishThreads + tid;
+    float g = 0.f;
+    if (i < f.P) {
+        if (peer.world > 1) {
+            const int phase = (int)(peer.epoch & 1u);
+            const unsigned long long* mine = peer.slots[peer.rank] + (int64_t)phase * peer.world * peer.stride;
+            unsigned long long w[GS_PEER_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < GS_PEER_MAX_WORLD; ++r)
+                if (r < peer.world) w[r] = ld_relaxed_sys_u64(mine + (int64_t)r * peer.stride + i);
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < GS_PEER_MAX_WORLD; ++r) {
+                if (r < peer.world) {
+                    uint32_t spin = 0;
+                    while ((uint32_t)(w[r] >> 32) != peer.epoch) {
+                        if (++spin > (1u << 27)) __trap();
+                        __nanosleep(20);
+                        w[r] = ld_relaxed_sys_u64(mine + (int64_t)r * peer.stride + i);
+                    }
+                    s += __uint_as_float((uint32_t)w[r]);   // rank order: identical on every rank
+                }
+            }
+            g = s * (1.0f / (float)peer.world);
+            grads[i] = g;
+        } else {
+            g = __ldcg(grads + i);
+        }
+    }
+    const int grp = i < po.wp ? 0 : (i < po.wv ? 1 : 2);
+    const double v = (double)g * (double)g;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double t = block_sum(grp == k ? v : 0.0, scratch);
+        if (tid == 0) sq_part[(int64_t)blockIdx.x * 3 + k] = t;
+    }
+    if (blockIdx.x == 0 && tid == 0 && ad.p) reinterpret_cast<int64_t*>(sq_part + (int64_t)gridDim.x * 3)[0] = *ad.step + 1;   // this step's count
+}
+
+__global__ void __launch_bounds__(kFinishThreads) finish_apply_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad,
+                                                                      const double* __restrict__ sq_part, double* __restrict__ metrics,
+                                                                      double* __restrict__ metrics_sum) {
+    __shared__ double sq[3];
+    __shared__ float adam_c[2];
+    const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next minibatch's update kernel may start its prologue
+    if (tid < 3) {
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += sq_part[(int64_t)b * 3 + tid];   // block order: the same sum in every block
+        sq[tid] = t;
+    }
+    const int64_t step = ad.p ? reinterpret_cast<const int64_t*>(sq_part + (int64_t)gridDim.x * 3)[0] : 0;
+    if (tid == 64 && ad.p) {
+        const double bc1 = 1.0 - pow((double)ad.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)ad.beta2, (double)step);
+        adam_c[0] = (float)((double)ad.lr / bc1);
+        adam_c[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const double total = sqrt(sq[0] + sq[1] + sq[2]);
+    double coef = 1.0;
+    if (f.max_norm > 0.f) { coef = (double)f.max_norm / (total + 1e-6); coef = coef > 1.0 ? 1.0 : coef; }
+    const float c = (float)coef;
+    const bool scale = coef < 1.0;
+    const int64_t i = (int64_t)blockIdx.x * kFinishThreads + tid;
+    if (i < po.total) {
+        float gi = __ldcg(grads + i);
+        if (scale) { gi *= c; grads[i] = gi; }
+        if (ad.p) {
+            const float m0 = ad.m[i], v0 = ad.v[i], p0 = ad.p[i];
+            const float mi = m0 + (gi - m0) * (1.f - ad.beta1);
+            const float vi = v0 * ad.beta2 + (1.f - ad.beta2) * gi * gi;
+            ad.m[i] = mi; ad.v[i] = vi;
+            const float denom = sqrtf(vi) / adam_c[1] + ad.eps;
+            ad.p[i] = p0 - adam_c[0] * (mi / denom);
+        }
+    }
+    if (blockIdx.x != 0) return;
+    if (tid == 64 && ad.p) *ad.step = step;
+    finalize_metrics_body(f.metric_partials, f.n_metric_cta, f.algo, f.H1, f.H2, f.track, f.vf_coef, f.ent_coef, f.normalize_adv, f.normalize_ret,
+                          f.dead, metrics);
+    if (tid == 0) {
+        metrics[GS_M_GRAD_NORM_ALL] = total;
+        metrics[GS_M_GRAD_NORM_BACKBONE] = sqrt(sq[0]);
+        metrics[GS_M_GRAD_NORM_POLICY] = sqrt(sq[1]);
+        metrics[GS_M_GRAD_NORM_VALUE] = sqrt(sq[2]);
+        metrics[GS_M_CLIP_COEF] = coef;
+    }
+    __syncthreads();
+    if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
+}
+
+// ---- sum over ranks of a short fp64 vector through the peer buffers (gs_peer_allreduce_f64) --------------------------------------
+// The minibatch moments of a pass (6 doubles per minibatch) have to be those of the GLOBAL minibatch.  An NCCL all-reduce of that vector
+// costs ~150 us on a side stream AND its kernel cannot share an SM with a persistent update CTA (registers), so it ran between two update
+// kernels and delayed one CTA -- hence the whole next launch -- by its duration: ~170 us per pass on 4 GPUs.  This one is a single block of
+// 256 threads and 30 registers that co-resides with the update kernel: every double travels as two {32-bit half, epoch} words (the protocol
+// of the gradient exchange), summed in rank order so every rank holds the identical result.
+constexpr int64_t kPeerMomDoubles = 8192;
+struct PeerMomDev {
+    int rank, world;
+    unsigned long long* slots[GS_PEER_MAX_WORLD];   // [2 phases][world][2 * kPeerMomDoubles] words
+    uint32_t epoch;
+};
+__device__ __forceinline__ uint32_t poll_word(const unsigned long long* src, uint32_t epoch) {
+    unsigned long long w = ld_relaxed_sys_u64(src);
+    uint32_t spin = 0;
+    while ((uint32_t)(w >> 32) != epoch) {
+        if (++spin > (1u << 27)) __trap();                      // a rank left the lock-step call sequence
+        __nanosleep(20);
+        w = ld_relaxed_sys_u64(src);
+    }
+    return (uint32_t)w;
+}
+__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(PeerMomDev pm, double* __restrict__ data, int n) {
+    const int tid = threadIdx.x;
+    const int64_t stride = 2 * kPeerMomDoubles;
+    const int64_t base = (int64_t)(pm.epoch & 1u) * pm.world * stride;
+    const uint32_t* halves = reinterpret_cast<const uint32_t*>(data);
+    for (int w = tid; w < 2 * n; w += 256) {
+        const unsigned long long word = ((unsigned long long)pm.epoch << 32) | (unsigned long long)halves[w];
+        for (int r = 0; r < pm.world; ++r) st_relaxed_sys_u64(pm.slots[r] + base + (int64_t)pm.rank * stride + w, word);
+    }
+    // own words are polled like everybody else's, so data[i] is overwritten only after both of its halves were read and posted
+    const unsigned long long* mine = pm.slots[pm.rank] + base;
+    for (int i = tid; i < n; i += 256) {
+        double s = 0.0;
+        for (int r = 0; r < pm.world; ++r) {
+            const uint32_t lo = poll_word(mine + (int64_t)r * stride + 2 * i, pm.epoch);
+            const uint32_t hi = poll_word(mine + (int64_t)r * stride + 2 * i + 1, pm.epoch);
+            s += __hiloint2double((int)hi, (int)lo);
+        }
+        data[i] = s;
+    }
 }
 
 // ---- minibatch moments of a rollout field (advantage / return batch normalisation) -------------------------------------
@@ -1078,9 +1227,10 @@ struct gs_peer {
     void* base = nullptr;               // own allocation: [2 phases][world][stride] 8-byte words {value bits, epoch}
     void* mapped[GS_PEER_MAX_WORLD] = {};   // peers' allocations (own rank: base)
     bool connected = false;
-    uint32_t epoch = 0;
+    uint32_t epoch = 0, mom_epoch = 0;  // call counters of gs_update_finish / gs_peer_allreduce_f64 (identical on every rank)
 };
 static size_t peer_slot_bytes(const gs_peer* p) { return ((size_t)2 * p->world * p->stride * 8 + 255) / 256 * 256; }
+static size_t peer_mom_bytes(const gs_peer* p) { return (size_t)2 * p->world * (2 * kPeerMomDoubles) * 8; }   // behind the gradient slots (+ 256)
 
 int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_peer_t** out, void* handle_out_host) {
     if (!out || !handle_out_host) GS_FAIL("gs_peer_create: NULL argument");
@@ -1092,7 +1242,7 @@ int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_
     gs_peer* p = new gs_peer();
     p->rank = rank; p->world = world_size; p->device = device;
     p->stride = (max_floats + 3) & ~3ll;
-    const size_t bytes = peer_slot_bytes(p) + 256;
+    const size_t bytes = peer_slot_bytes(p) + 256 + peer_mom_bytes(p);
     if (cudaMalloc(&p->base, bytes) != cudaSuccess) { delete p; GS_FAIL("gs_peer_create: cudaMalloc of %zu bytes failed", bytes); }
     cudaMemset(p->base, 0, bytes);
     cudaDeviceSynchronize();
@@ -1129,6 +1279,18 @@ int gs_peer_destroy(gs_peer_t* p) {
     for (int r = 0; r < p->world; ++r) if (r != p->rank && p->mapped[r]) cudaIpcCloseMemHandle(p->mapped[r]);
     if (p->base) cudaFree(p->base);
     delete p;
+    return 0;
+}
+
+int gs_peer_allreduce_f64(gs_peer_t* peer, double* data, int64_t n, void* stream) {
+    if (!peer || !data) GS_FAIL("gs_peer_allreduce_f64: NULL argument");
+    if (!peer->connected) GS_FAIL("gs_peer_allreduce_f64: peer group is not connected (gs_peer_connect)");
+    if (n <= 0 || n > kPeerMomDoubles) GS_FAIL("gs_peer_allreduce_f64: n = %lld outside 1..%lld", (long long)n, (long long)kPeerMomDoubles);
+    PeerMomDev pm = {};
+    pm.rank = peer->rank; pm.world = peer->world; pm.epoch = ++peer->mom_epoch;
+    for (int r = 0; r < peer->world; ++r) pm.slots[r] = (unsigned long long*)((char*)peer->mapped[r] + peer_slot_bytes(peer) + 256);
+    peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pm, data, (int)n);
+    GS_LAUNCH_CHECK();
     return 0;
 }
 
@@ -1182,8 +1344,19 @@ int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_fini
     }
     const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
     const unsigned blocks = (unsigned)((P + 63) / 64);
+    f.split = P > kFinishSplitP ? 1 : 0;
     update_finish_kernel<<<blocks, kFinishThreads, 0, (cudaStream_t)stream>>>(f, po, grads_flat, ad, pd, metrics, metrics_sum);
     GS_LAUNCH_CHECK();
+    if (f.split) {
+        // the partial vectors have been consumed: their memory holds the squared-norm partials (the next update kernel writes partials only
+        // after its griddepcontrol.wait, i.e. after finish_apply_kernel has completed)
+        double* sq_part = reinterpret_cast<double*>(w.grad_partials);
+        const unsigned nb = (unsigned)((P + kFinishThreads - 1) / kFinishThreads);
+        finish_receive_kernel<<<nb, kFinishThreads, 0, (cudaStream_t)stream>>>(f, po, grads_flat, ad, pd, sq_part);
+        GS_LAUNCH_CHECK();
+        finish_apply_kernel<<<nb, kFinishThreads, 0, (cudaStream_t)stream>>>(f, po, grads_flat, ad, sq_part, metrics, metrics_sum);
+        GS_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -75,6 +75,17 @@ class PeerGroup:
             self.close()
             raise N.EngineError(f"NVLink peer group could not be set up on every rank (rank {rank}: {err or 'ok'})")
 
+    MAX_F64 = 8192      # kPeerMomDoubles of csrc/update_kernels.cu
+
+    def allreduce_f64(self, t: torch.Tensor) -> bool:
+        """In-place rank-ordered sum of a short contiguous float64 CUDA tensor through the peer buffers (gs_peer_allreduce_f64, on the
+        current stream).  False when the tensor does not qualify (the caller falls back to the process group)."""
+        if not (self.handle and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= self.MAX_F64):
+            return False
+        N = self._N
+        N.check(N.lib().gs_peer_allreduce_f64(self.handle, N.ptr(t), int(t.numel()), N.stream()))
+        return True
+
     def close(self) -> None:
         if self.handle:
             self._N.lib().gs_peer_destroy(self.handle)
@@ -105,10 +116,13 @@ def average_gradients(flat_grads: torch.Tensor, world_size: int, group=None) -> 
     return flat_grads
 
 
-def allreduce_moments(moments: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
-    """In-place sum over ranks of (sum, sumsq, count) triples (any leading shape)."""
+def allreduce_moments(moments: torch.Tensor, world_size: int, group=None, peer: "PeerGroup | None" = None) -> torch.Tensor:
+    """In-place sum over ranks of (sum, sumsq, count) triples (any leading shape): through the NVLink peer buffers when a peer group is given
+    (a one-block kernel that runs beside the update kernel), else an all-reduce of the process group.  The choice depends only on the
+    tensor's shape and on the run's configuration, so every rank takes the same path."""
     if world_size > 1:
-        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+        if peer is None or not peer.allreduce_f64(moments):
+            dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
     return moments
 
 

@@ -358,6 +358,11 @@ typedef struct gs_peer gs_peer_t;
 int gs_peer_create(int rank, int world_size, int64_t max_floats, int device, gs_peer_t** out, void* handle_out_host);
 int gs_peer_connect(gs_peer_t* peer, const void* all_handles_host /* world_size * GS_PEER_HANDLE_BYTES, rank order */);
 int gs_peer_destroy(gs_peer_t* peer);
+/* In-place sum over the ranks of a short fp64 vector (n <= 8192; e.g. the (sum, sumsq, count) moments of a pass's minibatches, so that
+ * "batch" advantage normalisation -- agents/ppo/ppo_agent.py:47-48 -- sees the GLOBAL minibatch), exchanged through the peer buffers by a
+ * one-block kernel that co-resides with the update kernel; rank-ordered sum: every rank holds the identical result.  Every rank must make
+ * the same sequence of calls. */
+int gs_peer_allreduce_f64(gs_peer_t* peer, double* data, int64_t n, void* stream);
 int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch /* the deferred step's minibatch */, const gs_finish_t* fin,
                      float* grads_flat, const gs_adam_t* adam /* nullable: no optimizer step */,
                      gs_peer_t* peer /* nullable: single rank */, double* metrics, double* metrics_sum /* nullable */,

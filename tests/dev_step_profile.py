@@ -8,9 +8,10 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import bench
-args = argparse.Namespace(n_envs=65536, n_steps=128, batch_size=1048576, n_epochs=10, model_id=os.environ.get("GS_MODEL", "mlp_64x64"), track_activations=1)
+args = argparse.Namespace(n_envs=int(os.environ.get("GS_DEV_ENVS", "65536")), n_steps=128, batch_size=1048576, n_epochs=10, model_id=os.environ.get("GS_MODEL", "mlp_64x64"),
+                          track_activations=1, config=os.environ.get("GS_DEV_CONFIG", "c2"))
 agent, cfg = bench.build_agent_for_bench(args, rank, world)
-for _ in range(3):
+for _ in range(int(os.environ.get("GS_DEV_WARM", "3"))):
     agent.train_one_rollout()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity

@@ -1,6 +1,7 @@
 """Run under torchrun with >= 2 GPUs.  Checks of the NVLink peer gradient exchange fused into gs_update_finish:
   1. stress: 400 back-to-back exchanges of random per-rank gradients (no optimizer) — every rank must hold the bit-identical
-     mean, equal to the rank-ordered fp32 sum computed from an all_gather of the inputs;
+     mean, equal to the rank-ordered fp32 sum computed from an all_gather of the inputs; then gs_peer_allreduce_f64 (the moments
+     exchange) against the process group's all-reduce;
   2. training: a sharded CartPole PPO job through the peer path keeps bit-identical weights on every rank, and one iteration
      from identical state agrees with the NCCL generic path to rounding (state is re-synchronised before every iteration so
      sampling flips cannot amplify rounding differences).
@@ -51,6 +52,27 @@ def stress(rank, world, dev):
                 ref = ref + parts[r]
             ref = ref * (1.0 / world)
             assert torch.equal(model.flat_grads, ref), f"stress {it}: max diff {(model.flat_grads - ref).abs().max().item()}"
+    torch.cuda.synchronize()
+    moments(rank, world, dev, agent._peer)
+
+
+def moments(rank, world, dev, peer):
+    """gs_peer_allreduce_f64 against the process group's all-reduce: same values (to the last bits of a different summation order), identical
+    on every rank, over back-to-back calls of different lengths."""
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    for it in range(60):
+        n = (6, 48, 480, 768, 8192)[it % 5]
+        x = torch.randn(n, generator=g, device=dev, dtype=torch.float64) * (1.0 + it)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        y = x.clone()
+        assert peer.allreduce_f64(y), "peer all-reduce refused a qualifying tensor"
+        torch.testing.assert_close(y, ref, rtol=1e-14, atol=1e-12)
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y)
+        for r in range(1, world):
+            assert torch.equal(ys[0], ys[r]), f"moments {it}: rank {r} differs from rank 0"
+    assert not peer.allreduce_f64(torch.zeros(8193, dtype=torch.float64, device=dev))      # too long: the caller falls back
     torch.cuda.synchronize()
 
 
