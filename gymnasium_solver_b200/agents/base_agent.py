@@ -505,9 +505,11 @@ class BaseAgent(nn.Module):
             main.wait_event(st["ready"][c])
             for k in range(lo, hi):
                 self.training_step(batches[k], k)
-                # one gather of the next pass per step; the last step of the pass gets none, so the pass's all-reduce (queued with
-                # its final gather, one step earlier) has a whole step to complete
-                take = 2 if k == hi - 2 else (0 if k == hi - 1 else 1)
+                # the gathers of the next pass are queued two per step from the pass's first step on, so they -- and the pass's moment
+                # exchange, queued with the last of them -- are done by mid-pass on every rank: the exchange waits for the SLOWEST rank's
+                # side stream, and with one gather per step it finished ~200 us after the pass boundary on 8 GPUs (measured: the per-pass
+                # term of the 1 -> 8 GPU step-time difference)
+                take = int(os.environ.get("GS_GATHERS_PER_STEP", "2"))
                 for _ in range(take):
                     if nxt:
                         gather(c + 1, nxt.pop(0))

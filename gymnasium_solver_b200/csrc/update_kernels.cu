@@ -476,6 +476,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define GS_FT(k) do { } while (0)
 #endif
+constexpr int64_t kFinishSplitP = 8192;  // models above this finish grid-wide (finish_receive_kernel / finish_apply_kernel)
 constexpr int kFinishThreads = 1024;    // phase A: 64 parameters x 16 groups of partial vectors per block
 constexpr int kFinishGroups = kFinishThreads / 64;
 __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad, PeerDev peer,
@@ -498,6 +499,17 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
         const double bc2 = 1.0 - pow((double)ad.beta2, (double)step);
         adam_c[0] = (float)((double)ad.lr / bc1);
         adam_c[1] = (float)sqrt(bc2);
+    }
+    // The metric vector of the step (slots below GS_M_GRAD_NORM_ALL, batch count, return-normalisation slots) depends only on the update
+    // kernel's metric partials: one EXTRA block (the grid's last; it takes no ticket) computes it beside the gradient path instead of the
+    // last reducing block after it (5 of that block's 12 serial microseconds).  Large models: finish_apply_kernel's block 0 does it.
+    const unsigned n_reduce = f.split ? gridDim.x : gridDim.x - 1;
+    if (blockIdx.x >= n_reduce) {
+        finalize_metrics_body(f.metric_partials, f.n_metric_cta, f.algo, f.H1, f.H2, f.track, f.vf_coef, f.ent_coef, f.normalize_adv, f.normalize_ret,
+                              f.dead, metrics);
+        __syncthreads();
+        if (metrics_sum && tid < GS_M_SCRATCH && (tid < GS_M_GRAD_NORM_ALL || tid > GS_M_CLIP_COEF)) metrics_sum[tid] += metrics[tid];
+        return;
     }
     // ---- phase A (every block): sum of the per-CTA partial vectors in a fixed order (16 contiguous groups of CTAs, then the
     //      groups in order); the result goes to grads (one rank) or straight into every rank's receive slot over NVLink
@@ -531,9 +543,9 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
             }
         }
     }
-    if (peer.world == 1) __threadfence();                       // several ranks: the last block polls the words themselves
+    if (peer.world == 1) __threadfence();                       // several ranks: the last block polls the gradient words themselves
     __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (tid == 0) is_last = (atomicAdd(f.ticket, 1u) == n_reduce - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
     if (f.split) { if (tid == 0) *f.ticket = 0u; return; }
@@ -568,13 +580,21 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
         __syncthreads();
         GS_FT(2);                                              // every rank's words received and summed
     }
-    // metric vector of the step (slots below GS_M_GRAD_NORM_ALL, batch count, return-normalisation slots)
-    finalize_metrics_body(f.metric_partials, f.n_metric_cta, f.algo, f.H1, f.H2, f.track, f.vf_coef, f.ent_coef, f.normalize_adv, f.normalize_ret,
-                          f.dead, metrics);
-    // group norms in a fixed order (utils/models.py:196-230), clip coefficient (torch.nn.utils.clip_grad_norm_)
+    // group norms in a fixed order (utils/models.py:196-230), clip coefficient (torch.nn.utils.clip_grad_norm_).  This kernel serves models of
+    // at most kFinishSplitP parameters: a thread owns <= 8 elements, requested together (one L2 round trip, not one per element) and kept
+    // in registers for the optimizer step.
+    constexpr int kPer = (int)(kFinishSplitP / kFinishThreads);
+    float g[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int64_t i = tid + (int64_t)k * kFinishThreads;
+        g[k] = i < po.total ? __ldcg(grads + i) : 0.f;          // other blocks wrote it in phase A: read through L2
+    }
     double part[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = tid; i < po.total; i += kFinishThreads) {
-        const double v = (double)__ldcg(grads + i);            // other blocks wrote it in phase A: read through L2
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int64_t i = tid + (int64_t)k * kFinishThreads;
+        const double v = (double)g[k];
         const int grp = i < po.wp ? 0 : (i < po.wv ? 1 : 2);
         part[grp] += v * v;
     }
@@ -603,26 +623,38 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
         float* __restrict__ pp = ad.p;
         float* __restrict__ pm = ad.m;
         float* __restrict__ pv = ad.v;
-#pragma unroll 4
-        for (int64_t i = tid; i < po.total; i += kFinishThreads) {
-            float gi = __ldcg(grads + i);
-            const float m0 = pm[i], v0 = pv[i], p0 = pp[i];
-            if (scale) { gi *= c; grads[i] = gi; }
-            const float mi = m0 + (gi - m0) * (1.f - ad.beta1);
-            const float vi = v0 * ad.beta2 + (1.f - ad.beta2) * gi * gi;
-            pm[i] = mi; pv[i] = vi;
-            const float denom = sqrtf(vi) / bc2_sqrt + ad.eps;
-            pp[i] = p0 - step_size * (mi / denom);
+        float m0[kPer], v0[kPer], p0[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t i = tid + (int64_t)k * kFinishThreads;
+            if (i < po.total) { m0[k] = pm[i]; v0[k] = pv[i]; p0[k] = pp[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t i = tid + (int64_t)k * kFinishThreads;
+            if (i < po.total) {
+                float gi = g[k];
+                if (scale) { gi *= c; grads[i] = gi; }
+                const float mi = m0[k] + (gi - m0[k]) * (1.f - ad.beta1);
+                const float vi = v0[k] * ad.beta2 + (1.f - ad.beta2) * gi * gi;
+                pm[i] = mi; pv[i] = vi;
+                const float denom = sqrtf(vi) / bc2_sqrt + ad.eps;
+                pp[i] = p0[k] - step_size * (mi / denom);
+            }
         }
     } else if (scale) {
-        for (int64_t i = tid; i < po.total; i += kFinishThreads) grads[i] = __ldcg(grads + i) * c;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t i = tid + (int64_t)k * kFinishThreads;
+            if (i < po.total) grads[i] = g[k] * c;
+        }
     }
     __syncthreads();
     GS_FT(3);                                                  // metrics, norms, clip, Adam
 #ifdef GS_FINISH_TRACE
     if (tid == 0) atomicAdd(&g_fin_trace[7], 1ull);
 #endif
-    if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
+    if (metrics_sum && tid >= GS_M_GRAD_NORM_ALL && tid <= GS_M_CLIP_COEF) metrics_sum[tid] += metrics[tid];   // the slots this block wrote
 }
 
 // ---- the step tail of LARGE models, grid-wide (P > kFinishSplitP) ---------------------------------------------------------------------
@@ -631,7 +663,6 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
 //   finish_receive_kernel: every block receives / reads its 1024 gradient elements and writes the squared-norm partials of the three groups;
 //   finish_apply_kernel:   every block sums those partials in block order (identical everywhere), clips and applies Adam to its elements;
 //                          block 0 also finalises the metric vector.
-constexpr int64_t kFinishSplitP = 8192;
 __global__ void __launch_bounds__(kFinishThreads) finish_receive_kernel(FinishDev f, ParamOffsets po, float* __restrict__ grads, AdamDev ad, PeerDev peer,
                                                                         double* __restrict__ sq_part /* [gridDim.x][3] + step snapshot */) {
     __shared__ double scratch[32];
@@ -1343,8 +1374,8 @@ int gs_update_finish(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_fini
         for (int r = 0; r < peer->world; ++r) pd.slots[r] = (unsigned long long*)peer->mapped[r];
     }
     const ParamOffsets po = param_offsets(mlp->obs_dim, mlp->hidden1, mlp->hidden2, mlp->n_actions, mlp->has_value);
-    const unsigned blocks = (unsigned)((P + 63) / 64);
     f.split = P > kFinishSplitP ? 1 : 0;
+    const unsigned blocks = (unsigned)((P + 63) / 64) + (f.split ? 0u : 1u);     // + the metrics block
     update_finish_kernel<<<blocks, kFinishThreads, 0, (cudaStream_t)stream>>>(f, po, grads_flat, ad, pd, metrics, metrics_sum);
     GS_LAUNCH_CHECK();
     if (f.split) {
