@@ -174,7 +174,7 @@ class BaseAgent(nn.Module):
         self._ws_bytes = N.lib().gs_update_workspace_bytes(C.byref(mlp), self.device.index, int(self.local_batch_size))
         if self._ws_bytes <= 0:
             raise N.EngineError(N.lib().gs_last_error().decode())
-        self._workspace = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+        self._workspace = torch.zeros(self._ws_bytes, dtype=torch.uint8, device=self.device)   # clean: steps run with defer_reduce = 2 (no memset node)
         self._metrics_dev = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
         self._metrics_sum = torch.zeros(N.N_METRICS, dtype=torch.float64, device=self.device)
         self._metrics_n = 0

@@ -31,7 +31,7 @@ class PPOAgent(BaseAgent):
         hp.vf_coef, hp.ent_coef = float(self.vf_coef), float(self.ent_coef)
         hp.normalize_adv = int(cfg.normalize_advantages == "batch")
         hp.track_activations = int(bool(getattr(cfg, "track_activations", True)))
-        b.struct.defer_reduce = int(defer)
+        b.struct.defer_reduce = 2 if defer else 0          # 2: the agent's workspace is kept clean (base_agent: torch.zeros)
         adv_mom = moments[0:3] if moments is not None else None     # None on one rank: taken in the step's own gather pass
         with torch.cuda.device(self.device):
             N.check(N.lib().gs_ppo_step(C.byref(mlp), C.byref(b.struct), C.byref(hp), N.ptr(adv_mom), N.ptr(model.flat_grads),

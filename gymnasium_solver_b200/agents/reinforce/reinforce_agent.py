@@ -29,7 +29,7 @@ class REINFORCEAgent(BaseAgent):
         hp.policy_targets = 0 if cfg.policy_targets == "returns" else 1
         hp.normalize_adv, hp.normalize_returns = self._step_moments()
         hp.track_activations = int(bool(getattr(cfg, "track_activations", True)))
-        b.struct.defer_reduce = int(defer)
+        b.struct.defer_reduce = 2 if defer else 0          # 2: the agent's workspace is kept clean (base_agent: torch.zeros)
         adv_mom = moments[0:3] if moments is not None else None     # [0:3] adv, [3:6] ret; None: the step's own gather pass
         ret_mom = moments[3:6] if moments is not None else None
         with torch.cuda.device(self.device):

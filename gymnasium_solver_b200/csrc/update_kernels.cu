@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(kFinishThreads) update_finish_kernel(FinishDev
                               f.dead, metrics);
         __syncthreads();
         if (metrics_sum && tid < GS_M_SCRATCH && (tid < GS_M_GRAD_NORM_ALL || tid > GS_M_CLIP_COEF)) metrics_sum[tid] += metrics[tid];
+        if (f.track)                                            // consumed: leave the dead-unit counters zeroed for the next step
+            for (int i = tid; i < f.H1 + f.H2; i += kFinishThreads) const_cast<uint32_t*>(f.dead)[i] = 0u;
         return;
     }
     // ---- phase A (every block): sum of the per-CTA partial vectors in a fixed order (16 contiguous groups of CTAs, then the
@@ -757,6 +759,8 @@ __global__ void __launch_bounds__(kFinishThreads) finish_apply_kernel(FinishDev 
     }
     __syncthreads();
     if (metrics_sum && tid < GS_M_SCRATCH) metrics_sum[tid] += metrics[tid];
+    if (f.track)
+        for (int i = tid; i < f.H1 + f.H2; i += kFinishThreads) const_cast<uint32_t*>(f.dead)[i] = 0u;
 }
 
 // ---- sum over ranks of a short fp64 vector through the peer buffers (gs_peer_allreduce_f64) --------------------------------------
@@ -1035,7 +1039,11 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
     const float* mf1 = (hp.normalize_ret && !ret_mom) ? b.ret : nullptr;
     // dead-unit counters and the moment scratch are adjacent in the workspace: one memset node covers both
     // (+ the ticket counter of gs_update_finish behind the moments)
-    if (track || mf0 || mf1 || b.defer_reduce) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead) + 64, st));
+    // defer_reduce == 2: the caller guarantees a clean workspace (zero-initialised once; every finishing kernel leaves the dead-unit
+    // counters and the ticket zeroed), so no memset node sits between the previous step tail and this update kernel -- with one in between
+    // the programmatic dependent launch does not pair the two kernels and the update kernel's prologue runs after the tail, not under it
+    const bool clean = b.defer_reduce == 2 && !mf0 && !mf1;
+    if (!clean && (track || mf0 || mf1 || b.defer_reduce)) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead) + 64, st));
     if (mf0) adv_mom = w.sq;
     if (mf1) ret_mom = w.sq + 3;
     const bool tensor_path = tensor_path_for(C::H1, C::H2, md.act, md.D, b.T, b.N);
@@ -1089,6 +1097,7 @@ static int launch_update_cfg(const gs_mlp_t* m, const BatchDev& b, const HpDev& 
                                                                                   track ? 1 : 0, hp.vf_coef, hp.ent_coef, hp.normalize_adv,
                                                                                   hp.normalize_ret, w.dead, metrics);
     GS_LAUNCH_CHECK();
+    if (track) GS_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)((char*)w.sq - (char*)w.dead), st));   // every path leaves the counters clean
     return 0;
 }
 

@@ -158,7 +158,10 @@ typedef struct gs_batch {
      * step skips its gather pass.  Anything else about the batch must be unchanged between the two calls. */
     int32_t prepared;
     /* 1 = stop after the update kernel: the per-CTA partial gradients / metric partials stay in the workspace and
-     * gs_update_finish completes the step (ordered reduction, gradient all-reduce, metrics, clip, Adam) in one launch. */
+     * gs_update_finish completes the step (ordered reduction, gradient all-reduce, metrics, clip, Adam) in one launch.
+     * 2 = the same, and the caller guarantees a CLEAN workspace: zero-initialised before its first use and only ever used by complete
+     * steps (every finishing kernel leaves the counters it consumed zeroed).  The step then enqueues no memset, so the update kernel is
+     * launched programmatically right under the previous gs_update_finish. */
     int32_t defer_reduce;
     /* Optional (nullable) caller-owned buffer of n uint32 time-major sample offsets.  gs_batch_prepare writes it, a step
      * with prepared = 1 reads it; NULL = the workspace's own buffer (one minibatch at a time).  Lets a caller prepare every
