@@ -117,9 +117,15 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
-__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, uint64_t len, uint64_t key) {
+// domain width of the permutation of [0, len): the smallest bits >= 2 with 2^bits >= len
+__host__ __device__ __forceinline__ int feistel_bits(uint64_t len) {
     int bits = 2;
     while ((1ull << bits) < len) bits += 1;
+    return bits;
+}
+// `bits` = feistel_bits(len) when the caller has it (a per-launch constant: the search costs ~60 instructions per sample), else 0
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, uint64_t len, uint64_t key, int bits = 0) {
+    if (bits <= 0) bits = feistel_bits(len);
     const int lb = bits >> 1, rb = bits - lb;
     const uint32_t lmask = (uint32_t)((1ull << lb) - 1), rmask = (uint32_t)((1ull << rb) - 1);
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);

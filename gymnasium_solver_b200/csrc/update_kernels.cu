@@ -1132,6 +1132,7 @@ static BatchDev to_dev(const gs_batch_t* b) {
     d.prepared = b->prepared;
     d.defer_reduce = b->defer_reduce;
     d.offsets = b->offsets;
+    d.perm_bits = b->perm_len > 0 ? feistel_bits((uint64_t)b->perm_len) : 0;
     return d;
 }
 

@@ -30,6 +30,7 @@ struct BatchDev {
     int prepared;          // gs_batch_prepare already wrote the sample offsets of this minibatch into the workspace
     int defer_reduce;      // leave the per-CTA partials in the workspace: gs_update_finish completes the step
     uint32_t* offsets;     // nullable: caller-owned offsets buffer (instead of the workspace's)
+    int perm_bits;         // feistel_bits(perm_len), computed once on the host (0: unknown)
 };
 
 struct HpDev {
@@ -40,9 +41,13 @@ struct HpDev {
 __device__ __forceinline__ int64_t sample_offset(const BatchDev& b, int64_t pos) {
     int64_t i;
     if (b.idx) i = b.idx[pos];
-    else if (b.perm_len > 0) i = (int64_t)feistel_permute((uint64_t)(b.perm_offset + pos), (uint64_t)b.perm_len, b.perm_key);
+    else if (b.perm_len > 0) i = (int64_t)feistel_permute((uint64_t)(b.perm_offset + pos), (uint64_t)b.perm_len, b.perm_key, b.perm_bits);
     else i = b.perm_offset + pos;
     if (b.idx_map) i = b.idx_map[i];
+    if ((uint64_t)i < (1ull << 32)) {              // 32-bit division (a 64-bit one by a runtime divisor is ~100 instructions)
+        const uint32_t e = (uint32_t)i / (uint32_t)b.T, t = (uint32_t)i - e * (uint32_t)b.T;
+        return (int64_t)t * b.N + e;
+    }
     const int64_t e = i / b.T, t = i - e * b.T;   // env-major id -> (env, step)
     return t * b.N + e;                            // time-major offset
 }
