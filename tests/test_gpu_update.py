@@ -323,13 +323,24 @@ def test_update_errors_fail_loudly():
 @pytest.mark.parametrize("algo", ["ppo", "reinforce"])
 @pytest.mark.parametrize("n,D,A,activation", [(96, 4, 2, "relu"), (128, 4, 2, "relu"), (129, 6, 3, "relu"), (1000, 2, 3, "tanh"), (40000, 4, 2, "relu")])
 def test_tensor_core_and_simt_update_kernels_agree(algo, n, D, A, activation):
-    """64x64 network: the tcgen05 (3xTF32, TMEM accumulators) kernel and the fp32 FMA-pipe kernel implement the same
+    """64x64 network: the tcgen05 (fp16x3, TMEM accumulators) kernel and the fp32 FMA-pipe kernel implement the same
     contract; both must match the fp32 torch oracle, and each other far inside the 1e-4 bar."""
+    _tensor_core_vs_simt(algo, n, D, A, activation, 64)
+
+
+@pytest.mark.parametrize("hidden,n,D,A,algo", [(128, 40000, 6, 3, "ppo"), (256, 129, 2, 3, "ppo"), (256, 40000, 2, 3, "ppo"), (256, 70000, 4, 2, "reinforce")])
+def test_wide_tensor_core_update_kernels_agree_with_simt_and_oracle(hidden, n, D, A, algo):
+    """128x128 (one tile set of update_f16_kernel) and 256x256 (update_wide_kernel + wgrad_wide_kernel: streamed W2, stored operand
+    tiles) on minibatches of several tiles per CTA: same bar against the fp32 torch oracle and the FMA-pipe kernel."""
+    _tensor_core_vs_simt(algo, n, D, A, "relu", hidden)
+
+
+def _tensor_core_vs_simt(algo, n, D, A, activation, hidden):
     import engine_api as E
     from gymnasium_solver_b200 import _native as N
 
     g = torch.Generator().manual_seed(n + D)
-    p = P.random_params(D, (64, 64), A, seed=n, has_value=True)
+    p = P.random_params(D, (hidden, hidden), A, seed=n, has_value=True)
     import math
     obs = _away_from_kinks(p, torch.randn(1, n, D, generator=g), activation, g)
     actions = torch.randint(0, A, (1, n), generator=g)
