@@ -360,8 +360,8 @@ def kernel_rooflines(agent, cfg, dev):
 
     t = timed(one_collect, reps=5)
     cbytes = (34 + 12) * T * n
-    out["collect"] = {"kernel": "collect_kernel<64,64,64,CartPole> + GAE + stats", "bound": "hbm", "achieved": cbytes / t / 1e9,
-                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": tr("collect_kernel"),
+    out["collect"] = {"kernel": "collect_f16_kernel<64, CartPole> (tcgen05 forward) + GAE + stats" if hd == (64, 64) else "collect kernel + GAE + stats", "bound": "hbm", "achieved": cbytes / t / 1e9,
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cbytes / t / 1e9 / peaks["hbm_gbs"], "traffic": tr("collect_f16_kernel" if hd in ((64, 64), (128, 128)) else "collect_kernel"),
                       "env_steps_per_s": T * n / t, "avg_call_s": t,
                       "note": "whole RolloutCollector.collect() call (collect kernel + GAE + moments); compute-bound, reported for reference"}
     return out
