@@ -206,7 +206,7 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
                         for (int kk = 0; kk < 2; ++kk) mma_f16(T + cAcc, dPlo + aoff + 2u * kk, dB + (uint64_t)(kk * 128), idFullT, kk ? 1u : later);
                     }
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) mma_f16(T + cAcc, dPhi + aoff + 2u * kk, dB + (uint64_t)(kk * 128), idFullT, (kk || !lo) ? 1u : later);
+                    for (int kk = 0; kk < 2; ++kk) mma_f16_ts(T + cAcc, T + cAhi + 16u * blk + 8u * kk, dB + (uint64_t)(kk * 128), idFullT, (kk || !lo) ? 1u : later);
                     mma_commit(&bars[BAR_EMPTY + slot]);
                     if (s == 15) mma_commit(done);
                 }
@@ -235,11 +235,9 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
             GS_WT(1, 4);
             if (elect_one()) {
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint64_t a0 = pass == 0 ? dPlo : dPhi;
+                for (int kk = 0; kk < 16; ++kk) mma_f16(T + cH, dPlo + kfeat(kk), dWSh + (uint64_t)(kk * 128), idHeads, kk ? 1u : 0u);
 #pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) mma_f16(T + cH, a0 + kfeat(kk), dWSh + (uint64_t)(kk * 128), idHeads, (pass | kk) ? 1u : 0u);
-                }
+                for (int kk = 0; kk < 16; ++kk) mma_f16_ts(T + cH, T + cAhi + 8u * kk, dWSh + (uint64_t)(kk * 128), idHeads, 1u);
                 mma_commit(&bars[BAR_OUT]);
             }
             __syncwarp();
@@ -357,13 +355,17 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         fence_before_sync();
     };
     auto warp_ready = [&](int which) {
+        tmem_st_wait();
         fence_proxy_async();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[which]);
     };
     // 16 columns of the row as (hi, lo) -> P
-    auto store_q = [&](int qt, const uint32_t (&hw)[8], const uint32_t (&lw)[8]) {
+    auto store_q = [&](int qt, const uint32_t (&hw)[8], const uint32_t (&lw)[8], bool to_tmem) {
+        // the hi half also goes to tensor memory (two fp16 per column): the K-major uses of the tile (forward, dgrad, heads) take A_hi from
+        // there, which spares shared memory -- the kernel's bottleneck -- a third of their operand reads
+        if (to_tmem) tmem_st8u(T + cAhi + 32 * cg + 8 * qt, hw);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const uint32_t o = my_off + (uint32_t)(((2 * qt + c) ^ sw) << 4);
@@ -373,7 +375,7 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
     };
     // forward stage: the row's 64 pre-activations -> relu -> (hi, lo) -> P, 16 columns at a time (the whole row in registers spilled);
     // returns the relu mask
-    auto fwd_stage = [&](bool valid, float& zs, float& zq, uint32_t (&dcnt)[2], uint64_t* release, uint32_t parity) -> uint64_t {
+    auto fwd_stage = [&](bool valid, float& zs, float& zq, uint32_t (&dcnt)[2], uint64_t* release, uint32_t parity) -> uint64_t {   // h1 / h2: both feed K-major MMAs
         uint64_t mask = 0ull;
 #pragma unroll
         for (int qt = 0; qt < 4; ++qt) {
@@ -402,12 +404,12 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
 #pragma unroll
             for (int e = 0; e < 8; ++e) split_pair(fmaxf(z[2 * e], 0.f), fmaxf(z[2 * e + 1], 0.f), hw[e], lw[e]);
             if (qt == 0 && release) mbar_wait(release, parity);
-            store_q(qt, hw, lw);
+            store_q(qt, hw, lw, true);
         }
         return mask;
     };
     // backward stage: d(loss)/d(activation) of the row * relu' -> (hi, lo) -> P
-    auto bwd_stage = [&](uint64_t mask, uint64_t* release, uint32_t parity) {
+    auto bwd_stage = [&](uint64_t mask, uint64_t* release, uint32_t parity, bool to_tmem) {
 #pragma unroll
         for (int qt = 0; qt < 4; ++qt) {
             float d[16];
@@ -420,7 +422,7 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
 #pragma unroll
             for (int e = 0; e < 8; ++e) split_pair(d[2 * e], d[2 * e + 1], hw[e], lw[e]);
             if (qt == 0 && release) mbar_wait(release, parity);
-            store_q(qt, hw, lw);
+            store_q(qt, hw, lw, to_tmem);
         }
     };
 
@@ -494,7 +496,7 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         mbar_wait(&bars[BAR_DH2], p);
         fence_after_sync();
         GS_WT(0, 7);
-        bwd_stage(mask2, &bars[BAR_WC], p);
+        bwd_stage(mask2, &bars[BAR_WC], p, true);       // dz2 feeds dgrad (K-major A)
         warp_ready(RDY_DZ2);
         GS_WT(0, 8);
         // ---- E: dz1 (over dz2: dgrad, W-d and the tile store are done once dh1 is complete) ---------------------------------------------
@@ -507,7 +509,7 @@ update_wide_kernel(MlpDev m, BatchDev b, HpDev hp, const double* __restrict__ ad
         mbar_wait(&bars[BAR_DH1], p);
         fence_after_sync();
         GS_WT(0, 9);
-        bwd_stage(mask1, nullptr, 0u);
+        bwd_stage(mask1, nullptr, 0u, false);           // dz1 is only read MN-major (W-b)
         warp_ready(RDY_DZ1);
         GS_WT(0, 10);
     }

@@ -36,7 +36,7 @@ constexpr uint32_t oPhi = 0, oPlo = kTile, oX = 2 * kTile, oWS = oX + kSlab, oRi
 constexpr uint32_t oTmem = oBars + 8 * kBars, oBH = oTmem + 16, oNcs = oBH + 16, oRed = oNcs + 32, oFr = oRed + 8 * PM_N, kSmemBytes = oFr + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 // TMEM columns
-constexpr uint32_t cAcc = 0, cH = 256, cW1 = 272, cWh = 304, cB2 = 336;
+constexpr uint32_t cAcc = 0, cH = 256, cW1 = 272, cWh = 304, cB2 = 336, cAhi = 368;   // cAhi: the hi half of the activation tile as TMEM A operand (128 columns)
 
 // wgrad kernel: ring of 32-sample slices of the four stored tiles
 constexpr int kGRing = 3;

@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2g_gpu_tests.log 2>&1; tail -3 gpurun_out/r2g_gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | cut -c1-400
-GS_DEV_ITERS=1 timeout 600 ncu --set full --clock-control none -k regex:"collect_f16|gae_kernel" -c 2 -o gpurun_out/r2g_collect_gae -f python tests/dev_step_profile.py > gpurun_out/r2g_ncu_collect.log 2>&1; tail -1 gpurun_out/r2g_ncu_collect.log
+timeout 600 python tests/dev_wide_check.py 19072 1048576 > gpurun_out/w2_check.log 2>&1; grep "rel L2" gpurun_out/w2_check.log
+GS_DEV_PROFILE=1 GS_DEV_HIDDEN=256 timeout 300 python tests/dev_update_time.py --child > gpurun_out/w1_time256.log 2>&1; grep "gs_ppo_step\|wide" gpurun_out/w1_time256.log | cut -c1-70,150-230
+timeout 600 python -m pytest tests/test_gpu_update.py -x -q 2>&1 | tail -1
