@@ -1,5 +1,7 @@
+# Scratch command list for one `gpurun -- 'bash scripts/_dev_run.sh'` call during development (edited per experiment; the GPU box has no shell).
+# The commands the round's evidence came from are kept in profiles/*.md; the multi-GPU ones are scripts/scale_configs.sh.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python tests/dev_wide_check.py 19072 1048576 > gpurun_out/w2_check.log 2>&1; grep "rel L2" gpurun_out/w2_check.log
-GS_DEV_PROFILE=1 GS_DEV_HIDDEN=256 timeout 300 python tests/dev_update_time.py --child > gpurun_out/w1_time256.log 2>&1; grep "gs_ppo_step\|wide" gpurun_out/w1_time256.log | cut -c1-70,150-230
-timeout 600 python -m pytest tests/test_gpu_update.py -x -q 2>&1 | tail -1
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/dev_gpu_tests.log 2>&1; tail -3 gpurun_out/dev_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/dev_bench_c2.json 2> gpurun_out/dev_bench_c2.err; tail -c 600 gpurun_out/dev_bench_c2.json
