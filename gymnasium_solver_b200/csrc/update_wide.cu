@@ -4,19 +4,22 @@
 // Same contract and the same fp16x3 arithmetic as update_f16.cu (hi = fp16(x), lo = fp16(x - hi); lo*hi + hi*lo + hi*hi with fp32
 // accumulation in TMEM; backward quantities carried for the SUM loss, 1/B applied when accumulators are folded; reference:
 // agents/ppo/ppo_agent.py:21-152, agents/reinforce/reinforce_agent.py:11-88).  What changes at H = 256 is where things fit:
-//   * W2 as operand tiles (hi + lo) is 256 KB -- more than an SM's shared memory.  `stage_w2_kernel` writes it ONCE per step into
-//     the workspace in the operand layout ([precision][64-column slab][256 rows][128 B, SWIZZLE_128B chunks]) and every CTA streams
-//     it through a 3 x 16 KB ring with `cp.async.bulk` (a loader warp, full / empty mbarriers): 16 stages per tile for the forward
-//     pass ([128 j-rows][64 k] blocks: K-major B, N = 128) and 16 for dgrad (64 j-rows x two 64-column slabs: MN-major B, N = 128).
+//   * W2 as operand tiles (hi + lo) is 256 KB -- more than an SM's shared memory.  `stage_w2_kernel` writes W2 (rows j) and W2^T (rows k)
+//     ONCE per step into the workspace in the operand layout ([precision][64-column slab][256 rows][128 B, SWIZZLE_128B chunks]) and every
+//     CTA streams them through a 3 x 16 KB ring with `cp.async.bulk` (a loader warp, full / empty mbarriers).  Both GEMM phases read B
+//     MN-major (K = row) with N = 256, so one ring stage is 32 K-rows of all four slabs (two K = 16 steps): 16 stages per tile for the
+//     forward pass (W2^T: lo blocks then hi blocks) and 16 for dgrad (W2).  CTAs walk the 16 blocks of a phase from rotated starts.
 //   * the layer-2 weight gradient needs a 256 x 256 fp32 accumulator = all 512 TMEM columns.  It gets its own kernel: the fused
 //     kernel stores the two operands of that product -- the h1 and dz2 tiles exactly as they sit in shared memory (256 KB per
-//     128-sample tile, `cp.async.bulk` shared -> global issued by the MMA warp in 16 KB pieces between the stages of the GEMM phase that follows) -- and `wgrad_wide_kernel`
-//     streams them back (4-stage ring of 32-sample slices, both operands MN-major straight from the stored bytes) into
-//     dW2 = dz2^T . h1 with M = 2 x 128, N = 256.  Every other gradient (dW1, b1, b2, heads) is a 16-column accumulator of the
-//     fused kernel, as in update_f16.cu; b2's is dz2^T . [ones] (the ones of the g16 group).
-//   * one activation buffer P ([128][256] hi + lo = 128 KB) holds h1, then h2, then dz2, then dz1; relu'(h1) survives as a 64-bit
-//     mask per thread, relu'(h2) is re-derived from the tile.  One 256-column accumulator serves z1, z2, dh2, dh1 in turn.
-// Thread = (sample row, 64-column slab); 16 compute warps + MMA warp + loader warp, one CTA per SM, persistent over the tiles.
+//     128-sample tile, `cp.async.bulk` shared -> global issued by the MMA warp in 16 KB pieces between the stages of the GEMM phase that
+//     follows) -- and `wgrad_wide_kernel` streams them back (3-stage ring of 32-sample slices, both operands MN-major straight from the
+//     stored bytes) into dW2 = dz2^T . h1 with M = 2 x 128, N = 256.  Every other gradient (dW1, b1, b2, heads) is a 16-column
+//     accumulator of the fused kernel, as in update_f16.cu; b2's is dz2^T . [ones] (the ones of the g16 group).
+//   * one activation buffer P ([128][256] hi + lo = 128 KB) holds h1, then h2, then dz2, then dz1; relu' of both layers survives as a
+//     64-bit mask per thread.  One 256-column accumulator serves z1, z2, dh2, dh1 in turn, so the MMA phases and the SIMT stages of a
+//     tile alternate.  The hi half of the tile is also kept in tensor memory (two fp16 per column) as the A operand of the K-major MMAs.
+// Thread = (sample row, 64-column slab), walking its slab 16 columns at a time; 16 compute warps + MMA warp + loader warp, one CTA per SM,
+// persistent over the tiles.  Measurements and the steps that led here: DESIGN.md section 3, profiles/r2_update_wide_ncu_details.md.
 #include <type_traits>
 
 #define GS_FAST_TRANSCENDENTALS
