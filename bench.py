@@ -132,8 +132,12 @@ def launches_per_step(cfg, world):
     per_rollout = 1 + 2 + 1 + 2 + (1 if tensor_path else 0)   # collect, obs/reward moments, gae, adv/ret moments, rollout_pack
     # tensor path: gather pass (offsets + batch moments; all of a rollout's up front when sharded), update kernel,
     # gs_update_finish (reduction + NVLink gradient mean + metrics + clip + Adam).  FMA-pipe path: batch moments, update, finish.
-    per_mb = 5 if wide else 3           # 256 x 256: + stage_w2_kernel and wgrad_wide_kernel (csrc/update_wide.cu)
-    return per_rollout + n_mb * per_mb
+    # per minibatch: gather pass + update kernel + step tail (one launch; three -- reduce, receive, apply -- above 8,192 parameters);
+    # 256 x 256: + stage_w2_kernel and wgrad_wide_kernel (csrc/update_wide.cu); several ranks: + one moment-exchange kernel per pass
+    hd = tuple(cfg.hidden_dims)
+    per_mb = 3 + (2 if hd in ((128, 128), (256, 256)) else 0) + (2 if wide else 0)
+    n_pass = int(cfg.n_epochs) if world > 1 else 0
+    return per_rollout + n_mb * per_mb + n_pass
 
 
 def run_b200(args):
