@@ -19,7 +19,7 @@ for ln in sass.splitlines():
     if m and cur:
         hist[cur][m.group(1)] += 1
 names = subprocess.run(["c++filt"], input="\n".join(hist), capture_output=True, text=True).stdout.splitlines()
-keys = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "LDGSTS", "LDL", "STL", "SYNCS", "BAR", "LDS", "STS", "LDG", "STG", "FFMA", "FMUL",
+keys = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UBLKCP", "LDGSTS", "LDL", "STL", "SYNCS", "BAR", "LDS", "STS", "LDG", "STG", "FFMA", "FMUL",
         "FADD", "F2FP", "HADD2", "MUFU", "SHFL", "DFMA", "DMUL", "DADD", "ATOMS", "ATOMG", "RED"]
 print("| kernel | SASS instructions | " + " | ".join(keys) + " |")
 print("|---|---|" + "---|" * len(keys))
