@@ -36,6 +36,7 @@ import torch.nn as nn
 from .. import _native as N
 from ..utils import distributed as D
 from ..utils.distributed import PeerGroup, allreduce_moments, average_gradients, shard_spec
+from .hyperparameter_mixin import HyperparameterMixin, RunConfigFile  # noqa: F401  (RunConfigFile: re-exported for launchers)
 from ..utils.environment import build_env_from_config
 from ..utils.optimizer_factory import EngineAdam, build_optimizer
 from ..utils.policy_factory import build_policy_from_env_and_config
@@ -119,7 +120,7 @@ class MetricsRecorder:
         self.history.append(dict(metrics))
 
 
-class BaseAgent(nn.Module):
+class BaseAgent(HyperparameterMixin, nn.Module):
     def __init__(self, config, *, device=None, rank: Optional[int] = None, world_size: Optional[int] = None):
         super().__init__()
         self.config = config
@@ -251,14 +252,7 @@ class BaseAgent(nn.Module):
             self._optimizer = self.configure_optimizers()
         return self._optimizer
 
-    def _change_optimizers_lr(self, lr: float) -> None:
-        for group in self.optimizers().param_groups:
-            group["lr"] = lr
-
-    def set_hyperparameter(self, name: str, value: float) -> None:
-        setattr(self, name, value)
-        if name == "policy_lr":
-            self._change_optimizers_lr(value)
+    # _change_optimizers_lr / set_hyperparameter / _read_hyperparameters_from_run / _log_hyperparameters: HyperparameterMixin
 
     def _as_engine_batch(self, batch) -> EngineBatch:
         """Accept the engine's own minibatch descriptor or a reference-style gathered RolloutTrajectory (flat tensors)."""
@@ -609,7 +603,9 @@ class BaseAgent(nn.Module):
         reason = ""
         try:
             while True:
-                # on_train_epoch_start: budget check before collecting (reference agents/base_agent.py:306-320)
+                # on_train_epoch_start: live hyper-parameters (:297-302), then the budget check before collecting (:306-320)
+                self._read_hyperparameters_from_run()
+                self._log_hyperparameters()
                 if cfg.max_env_steps is not None:
                     cur = col.total_steps * self.world_size
                     nxt = int(cfg.n_envs) * int(cfg.n_steps)
@@ -684,6 +680,8 @@ class BaseAgent(nn.Module):
         """reference agents/base_agent.py:284-328: env-step budget check, then collect this epoch's rollout.  False = stop."""
         cfg, col = self.config, self.get_rollout_collector("train")
         self.timings.start("on_train_epoch_start", values=self._host_counters("train"))
+        self._read_hyperparameters_from_run()      # the user may have edited the run's config.json (reference :297-299)
+        self._log_hyperparameters()
         if cfg.max_env_steps is not None:
             cur, nxt = col.total_steps * self.world_size, int(cfg.n_envs) * int(cfg.n_steps)
             if cur + nxt > cfg.max_env_steps:

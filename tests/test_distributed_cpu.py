@@ -45,6 +45,23 @@ def _worker(rank, world, port, out):
         stop_seq = [agree_any(rank == 1 and epoch == 3, torch.device("cpu"), world) for epoch in range(5)]
         assert stop_seq == [False, False, False, True, False]
         assert broadcast_value(10.0 + rank, torch.device("cpu"), world) == 10.0
+        # live hyper-parameters: every rank applies RANK 0's reading of the run's config file (the ranks' weights must stay identical)
+        from gymnasium_solver_b200.agents.hyperparameter_mixin import HyperparameterMixin
+
+        class _Run:
+            def load_config(self): return {"policy_lr": 1e-3 * (rank + 1), "clip_range": 0.2}
+
+        class _Cfg:
+            policy_lr, clip_range = 5e-3, 0.2
+
+        class _Agent(HyperparameterMixin):
+            def __init__(self):
+                self.config, self.run, self.rank, self.world_size, self.policy_lr, self._optimizer = _Cfg(), _Run(), rank, world, 5e-3, None
+            def optimizers(self): return []
+
+        a = _Agent()
+        a._read_hyperparameters_from_run()
+        assert a.policy_lr == 1e-3 and a.config.policy_lr == 1e-3, a.policy_lr
         out.put((rank, local.numpy(), grads.numpy(), x.numpy(), mom.numpy(), t))
     finally:
         dist.destroy_process_group()

@@ -3,7 +3,7 @@
 The reference's test files are copied at run time from /root/reference/tests into a temporary directory (never into this repo) next
 to a conftest that maps the module names they import (``utils.samplers``, ``utils.dataloaders``, ``utils.datasets``,
 ``utils.rollouts``, ``utils.distributions``, ``utils.models``, ``utils.policy_factory``, ``trainer_callbacks.hyperparameter_scheduler``,
-``gym_wrappers.env_wrapper_registry``) onto ``gymnasium_solver_b200``; pytest runs them in a subprocess.  These are the tests SURVEY.md §4
+``gym_wrappers.env_wrapper_registry``, ``agents.hyperparameter_mixin``) onto ``gymnasium_solver_b200``; pytest runs them in a subprocess.  These are the tests SURVEY.md §4
 lists as passing on the reference and pinning behaviour the engine must reproduce.
 
 Build container only (skipped where /root/reference is absent: nothing on the GPU box reads the reference).  One test is deselected and
@@ -24,7 +24,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference 
 
 FILES = ["test_multipass_random_sampler.py", "test_epoch_shuffling.py", "test_index_dataset.py", "test_rollout_buffer.py",
          "test_masked_categorical.py", "test_models.py", "test_policy_factory_initialization.py", "test_schedulers.py",
-         "test_env_wrapper_registry.py"]
+         "test_env_wrapper_registry.py", "test_hyperparameter_mixin.py"]
 DESELECT = ["test_rollout_buffer.py::test_add_stores_observations_and_dtypes_correctly"]
 
 CONFTEST = '''
@@ -39,7 +39,8 @@ def pkg(name):
 def alias(name, target):
     sys.modules[name] = importlib.import_module(target)
 
-pkg("utils"); pkg("trainer_callbacks"); pkg("gym_wrappers")
+pkg("utils"); pkg("trainer_callbacks"); pkg("gym_wrappers"); pkg("agents")
+alias("agents.hyperparameter_mixin", E + ".agents.hyperparameter_mixin")
 for name, src in (("samplers", "samplers"), ("dataloaders", "dataloaders"), ("datasets", "dataloaders"), ("rollout_buffer", "rollout_buffer"),
                   ("rollouts", "rollout_buffer"), ("distributions", "distributions"), ("models", "models"), ("policy_factory", "policy_factory"),
                   ("rollout_stats", "rollout_stats"), ("torch", "torch"), ("policy_ops", "policy_ops"), ("model_registry", "model_registry")):
@@ -68,4 +69,4 @@ def test_reference_unit_tests_pass_against_the_engine_modules(tmp_path):
     assert r.returncode == 0, tail
     summary = [l for l in r.stdout.splitlines() if " passed" in l][-1]
     n_passed = int(summary.split(" passed")[0].split()[-1])
-    assert n_passed >= 64 and "failed" not in summary and "error" not in summary, summary
+    assert n_passed >= 65 and "failed" not in summary and "error" not in summary, summary

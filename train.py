@@ -64,6 +64,8 @@ def main(argv=None) -> int:
     ap.add_argument("--max-env-steps", type=int, default=None)
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--resume", default=None, help="checkpoint directory to resume from")
+    ap.add_argument("--run-dir", default=None, help="write config.json here and re-read it at every epoch start: edit policy_lr / clip_range / "
+                                                     "ent_coef / vf_coef / n_epochs while training runs (reference agents/hyperparameter_mixin.py:37-64)")
     args = ap.parse_args(argv)
     spec = args.config_id_opt or args.config_id
     if ":" not in spec:
@@ -87,6 +89,11 @@ def main(argv=None) -> int:
     agent = build_agent(config)
     if args.resume:
         agent.load_checkpoint(args.resume)
+    if args.run_dir:                                # rank 0 reads the file at every epoch start and broadcasts its reading
+        from gymnasium_solver_b200.agents.hyperparameter_mixin import RunConfigFile
+        agent.run = RunConfigFile(args.run_dir)
+        if int(os.environ.get("RANK", 0)) == 0 or not os.path.exists(agent.run.path):
+            agent.run.save_config(config)
 
     def log(row):
         if config.quiet:
