@@ -173,7 +173,22 @@ def stream() -> int:
 
 
 def mlp_struct(model) -> GsMlp:
-    """gs_mlp_t over the live nn.Parameter storage of an MLPActorCritic / MLPPolicy (utils/models.py)."""
+    """gs_mlp_t over the live nn.Parameter storage of an MLPActorCritic / MLPPolicy (utils/models.py).  Built once per parameter storage:
+    the struct only holds device pointers and shapes, and it is asked for twice per minibatch (walking the modules and validating eight
+    tensors cost ~30 us of host time per minibatch -- a fifth of a sharded 128 x 128 step on 8 GPUs)."""
+    key = tuple(int(t.data_ptr()) for t in model.parameters())
+    cached = getattr(model, "_gs_mlp_struct_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    s = _build_mlp_struct(model)
+    try:
+        object.__setattr__(model, "_gs_mlp_struct_cache", (key, s))
+    except Exception:
+        pass
+    return s
+
+
+def _build_mlp_struct(model) -> GsMlp:
     lin = [m for m in model.backbone if isinstance(m, torch.nn.Linear)]
     if len(lin) not in (1, 2):
         raise EngineError(f"engine supports 1 or 2 hidden layers, got {len(lin)}")
