@@ -303,8 +303,10 @@ int gs_rollout_pack(const gs_batch_t* batch, float* packed, void* stream);
  * zeroed by the call.  All-reduce moments, then call the step with them and batch->prepared = 1. */
 int gs_batch_prepare(const gs_mlp_t* mlp, const gs_batch_t* batch, int want_adv, int want_ret, double* moments,
                      void* workspace, int64_t workspace_bytes, void* stream);
-/* Kernel selection for gs_ppo_step / gs_reinforce_step: 0 (default) = tcgen05 tensor-core kernel where one exists (64x64
- * MLP: 3xTF32, fp32 TMEM accumulators), 1 = fp32 FMA-pipe kernel everywhere.  Env GS_UPDATE_IMPL=simt|tc sets the default. */
+/* Kernel selection for gs_ppo_step / gs_reinforce_step: 0 (default) = tcgen05 tensor-core kernels where they exist (64x64, 128x128 and
+ * relu 256x256 MLPs with obs_dim <= 7: kind::f16, fp16x3 split, fp32 TMEM accumulators -- the presets of utils/model_registry.py:20-31),
+ * 1 = fp32 FMA-pipe kernel everywhere.  Env GS_UPDATE_IMPL=simt|tc sets the default; GS_ROLLOUT_IMPL=simt does the same for the collect /
+ * policy_act kernels. */
 int gs_set_update_impl(int impl);
 int64_t gs_mlp_param_count(const gs_mlp_t* mlp);
 int gs_ppo_step(const gs_mlp_t* mlp, const gs_batch_t* batch, const gs_ppo_hparams_t* hp, const double* adv_moments,
